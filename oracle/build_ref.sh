@@ -1,0 +1,23 @@
+#!/usr/bin/env bash
+# Compile the UNMODIFIED reference CLI (src/*.cpp + kernels/*.cu) with nvcc for sm_100
+# straight from where the sources lie; outputs only into oracle/_ref/.
+# (The reference's CMakeLists pins sm_61, CMakeLists.txt:49-52; we do not run its build system.)
+# Nothing is copied from the reference tree.
+set -euo pipefail
+REF=${1:-/root/reference}
+OUT=${2:-$(dirname "$0")/_ref}
+mkdir -p "$OUT"
+STAMP="$OUT/.stamp"
+if [ -x "$OUT/FlashAttention_ref" ] && [ -f "$STAMP" ] && [ "$(cat "$STAMP")" = "$(cd "$REF" && find kernels src include -type f | sort | xargs md5sum | md5sum)" ]; then
+  echo "oracle/_ref up to date"; exit 0
+fi
+nvcc -O3 -std=c++17 --extended-lambda --expt-relaxed-constexpr \
+  -gencode arch=compute_100,code=sm_100 \
+  -I"$REF/include" -I"$REF/kernels" \
+  "$REF"/src/main.cpp "$REF"/src/utils.cpp \
+  "$REF"/kernels/f-attn.cu "$REF"/kernels/vanilla-attn.cu "$REF"/kernels/plain-attn.cu \
+  "$REF"/kernels/kernel_fa2_optimized.cu "$REF"/kernels/kernel_fa2_optimized_f16.cu \
+  "$REF"/kernels/f-attn2-backward.cu "$REF"/kernels/f-attn2-backward_f16.cu \
+  -o "$OUT/FlashAttention_ref"
+(cd "$REF" && find kernels src include -type f | sort | xargs md5sum | md5sum) > "$STAMP"
+echo "built $OUT/FlashAttention_ref"
