@@ -1,0 +1,438 @@
+// fa2_api.cu -- the C ABI of libfa2_b200.so (include/fa2_b200.h): argument checking, the
+// per-device workspace, TMA descriptor construction, the device-pointer entry points and the
+// host-pointer entry points with the batch*head partitioner across the GPUs of one box.
+//
+// Replaces, for the fa2 path only: host_flash_attention2_{forward,backward}{,_fp16}
+// (kernels/kernel_fa2_optimized.cu:351-423, kernels/f-attn2-backward.cu:384-485 and twins)
+// and the CuPy kernel wrappers.  No exit(): errors are returned.
+#include "../../include/fa2_b200.h"
+#include "fa2_common.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace fa2 {
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define FA2_CUDA(call)                                                                              \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+            return fail(FA2_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda link dependency)
+// ------------------------------------------------------------------------------------------
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+// 16-bit [BH][S][DP] tensor, box {64 cols, box_rows, 1 slab}, 128-byte swizzle, zero OOB fill.
+int make_tmap_16(CUtensorMap* tm, void* base, int BH, int S, int DP, int box_rows, int bf16) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return fail(FA2_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    cuuint64_t dims[3] = {static_cast<cuuint64_t>(DP), static_cast<cuuint64_t>(S), static_cast<cuuint64_t>(BH)};
+    cuuint64_t strides[2] = {static_cast<cuuint64_t>(DP) * 2, static_cast<cuuint64_t>(S) * DP * 2};
+    cuuint32_t box[3] = {64, static_cast<cuuint32_t>(box_rows), 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(tm, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, base, dims,
+                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(FA2_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return FA2_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// per-device arenas (grown on demand, kept until fa2_release_workspaces)
+// ------------------------------------------------------------------------------------------
+struct Arena {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+};
+constexpr int kMaxDevices = 64;
+std::mutex g_mu;
+Arena g_work[kMaxDevices];   // 16-bit operand copies, delta, lse_log2
+Arena g_io[kMaxDevices];     // fp32 device mirrors used by the host-pointer entry points
+
+int arena_reserve(Arena* arenas, int dev, size_t bytes, void** out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    Arena& a = arenas[dev];
+    if (a.bytes < bytes) {
+        if (a.ptr) {
+            FA2_CUDA(cudaDeviceSynchronize());
+            FA2_CUDA(cudaFree(a.ptr));
+            a.ptr = nullptr;
+            a.bytes = 0;
+        }
+        FA2_CUDA(cudaMalloc(&a.ptr, bytes));
+        a.bytes = bytes;
+    }
+    *out = a.ptr;
+    return FA2_OK;
+}
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct WorkLayout {
+    size_t off_q, off_k, off_v, off_do, off_delta, off_lse2, total;
+};
+WorkLayout work_layout(size_t rows, int DP, bool backward) {
+    WorkLayout w{};
+    const size_t t16 = align_up(rows * DP * 2, 1024);
+    const size_t vec = align_up(rows * 4, 1024);
+    size_t off = 0;
+    w.off_q = off; off += t16;
+    w.off_k = off; off += t16;
+    w.off_v = off; off += t16;
+    w.off_do = off; if (backward) off += t16;
+    w.off_delta = off; if (backward) off += vec;
+    w.off_lse2 = off; if (backward) off += vec;
+    w.total = off;
+    return w;
+}
+
+int check_shape(int B, int H, int S, int D) {
+    if (B <= 0 || H <= 0 || S <= 0 || D <= 0)
+        return fail(FA2_ERR_INVALID_ARGUMENT, "dimensions must be positive (B=%d H=%d S=%d D=%d)", B, H, S, D);
+    if (D != 32 && D != 64 && D != 128)
+        return fail(FA2_ERR_INVALID_ARGUMENT, "Unsupported head dimension %d (supported: 32, 64, 128)", D);
+    if (static_cast<long long>(B) * H > 0x7fffffffLL / 64)
+        return fail(FA2_ERR_INVALID_ARGUMENT, "B*H too large");
+    return FA2_OK;
+}
+int check_precision(int precision) {
+    if (precision != FA2_PRECISION_FP16 && precision != FA2_PRECISION_FP32 && precision != FA2_PRECISION_BF16)
+        return fail(FA2_ERR_INVALID_ARGUMENT, "unknown precision %d", precision);
+    return FA2_OK;
+}
+
+struct Prepared {
+    int dev = 0;
+    int BH = 0, S = 0, D = 0, DP = 0, bf16 = 0;
+    size_t rows = 0;
+    uint8_t* work = nullptr;
+    WorkLayout wl{};
+    float scale = 0.f, scale_log2 = 0.f;
+};
+
+int prepare(Prepared* pr, int B, int H, int S, int D, int precision, bool backward) {
+    int rc = check_shape(B, H, S, D);
+    if (rc) return rc;
+    rc = check_precision(precision);
+    if (rc) return rc;
+    FA2_CUDA(cudaGetDevice(&pr->dev));
+    if (pr->dev >= kMaxDevices) return fail(FA2_ERR_UNSUPPORTED, "device ordinal %d too large", pr->dev);
+    pr->BH = B * H; pr->S = S; pr->D = D; pr->DP = padded_head_dim(D);
+    pr->bf16 = (precision == FA2_PRECISION_BF16) ? 1 : 0;
+    pr->rows = static_cast<size_t>(pr->BH) * S;
+    pr->wl = work_layout(pr->rows, pr->DP, backward);
+    void* w = nullptr;
+    rc = arena_reserve(g_work, pr->dev, pr->wl.total, &w);
+    if (rc) return rc;
+    pr->work = static_cast<uint8_t*>(w);
+    pr->scale = 1.0f / sqrtf(static_cast<float>(D));
+    pr->scale_log2 = pr->scale * 1.4426950408889634f;
+    return FA2_OK;
+}
+
+int run_cast(const Prepared& pr, const float* Q, const float* K, const float* V, cudaStream_t st) {
+    FA2_CUDA(launch_cast_qkv(Q, K, V, pr.work + pr.wl.off_q, pr.work + pr.wl.off_k, pr.work + pr.wl.off_v, pr.rows,
+                             pr.D, pr.DP, pr.bf16, st));
+    return FA2_OK;
+}
+
+int run_fwd_main(const Prepared& pr, float* O, float* LSE, cudaStream_t st) {
+    FwdParams p{};
+    int rc;
+    if ((rc = make_tmap_16(&p.tm_q, pr.work + pr.wl.off_q, pr.BH, pr.S, pr.DP, 128, pr.bf16))) return rc;
+    if ((rc = make_tmap_16(&p.tm_k, pr.work + pr.wl.off_k, pr.BH, pr.S, pr.DP, 128, pr.bf16))) return rc;
+    if ((rc = make_tmap_16(&p.tm_v, pr.work + pr.wl.off_v, pr.BH, pr.S, pr.DP, 128, pr.bf16))) return rc;
+    p.O = O; p.LSE = LSE; p.BH = pr.BH; p.S = pr.S; p.D = pr.D;
+    p.scale = pr.scale; p.scale_log2 = pr.scale_log2; p.bf16 = pr.bf16;
+    FA2_CUDA(launch_fwd(p, st));
+    return FA2_OK;
+}
+
+int run_bwd_main(const Prepared& pr, const float* O, const float* dO, const float* LSE, float* dQ, float* dK,
+                 float* dV, cudaStream_t st) {
+    float* delta = reinterpret_cast<float*>(pr.work + pr.wl.off_delta);
+    float* lse2 = reinterpret_cast<float*>(pr.work + pr.wl.off_lse2);
+    FA2_CUDA(launch_bwd_prepass(O, dO, LSE, pr.work + pr.wl.off_do, delta, lse2, dQ, pr.rows, pr.D, pr.DP, pr.bf16,
+                                st));
+    BwdParams p{};
+    int rc;
+    if ((rc = make_tmap_16(&p.tm_q, pr.work + pr.wl.off_q, pr.BH, pr.S, pr.DP, 128, pr.bf16))) return rc;
+    if ((rc = make_tmap_16(&p.tm_k, pr.work + pr.wl.off_k, pr.BH, pr.S, pr.DP, 128, pr.bf16))) return rc;
+    if ((rc = make_tmap_16(&p.tm_v, pr.work + pr.wl.off_v, pr.BH, pr.S, pr.DP, 128, pr.bf16))) return rc;
+    if ((rc = make_tmap_16(&p.tm_do, pr.work + pr.wl.off_do, pr.BH, pr.S, pr.DP, 128, pr.bf16))) return rc;
+    p.lse_log2 = lse2; p.delta = delta; p.dQ = dQ; p.dK = dK; p.dV = dV;
+    p.BH = pr.BH; p.S = pr.S; p.D = pr.D; p.scale = pr.scale; p.scale_log2 = pr.scale_log2; p.bf16 = pr.bf16;
+    FA2_CUDA(launch_bwd(p, st));
+    return FA2_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// host-pointer path: one worker thread per device, each on its own contiguous slab range
+// ------------------------------------------------------------------------------------------
+struct HostJob {
+    const float *Q, *K, *V, *O_in, *dO, *LSE_in;
+    float *O, *LSE, *dQ, *dK, *dV;
+    int B, H, S, D, precision;
+    int mode;   // FA2_MODE_*
+};
+
+int host_worker(const HostJob& job, int dev, int bh0, int count, float* ms_out, std::string* err_out) {
+    auto run = [&]() -> int {
+        FA2_CUDA(cudaSetDevice(dev));
+        const size_t slab = static_cast<size_t>(job.S) * job.D;           // floats per (b,h)
+        const size_t n = slab * count, nl = static_cast<size_t>(job.S) * count;
+        const size_t tb = align_up(n * 4, 1024), lb = align_up(nl * 4, 1024);
+        const bool fwd = job.mode != FA2_MODE_BACKWARD, bwd = job.mode != FA2_MODE_FORWARD;
+        // io arena: Q K V O LSE [dO dQ dK dV]
+        const size_t total = 4 * tb + lb + (bwd ? 4 * tb : 0);
+        void* base = nullptr;
+        int rc = arena_reserve(g_io, dev, total, &base);
+        if (rc) return rc;
+        uint8_t* b8 = static_cast<uint8_t*>(base);
+        float* dQ_ = nullptr; float* dK_ = nullptr; float* dV_ = nullptr; float* ddO = nullptr;
+        float* dQin = reinterpret_cast<float*>(b8);
+        float* dKin = reinterpret_cast<float*>(b8 + tb);
+        float* dVin = reinterpret_cast<float*>(b8 + 2 * tb);
+        float* dO_ = reinterpret_cast<float*>(b8 + 3 * tb);
+        float* dL = reinterpret_cast<float*>(b8 + 4 * tb);
+        if (bwd) {
+            ddO = reinterpret_cast<float*>(b8 + 4 * tb + lb);
+            dQ_ = reinterpret_cast<float*>(b8 + 5 * tb + lb);
+            dK_ = reinterpret_cast<float*>(b8 + 6 * tb + lb);
+            dV_ = reinterpret_cast<float*>(b8 + 7 * tb + lb);
+        }
+        cudaStream_t st;
+        FA2_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        cudaEvent_t e0, e1;
+        FA2_CUDA(cudaEventCreate(&e0));
+        FA2_CUDA(cudaEventCreate(&e1));
+        const size_t off = static_cast<size_t>(bh0) * slab, offl = static_cast<size_t>(bh0) * job.S;
+        FA2_CUDA(cudaMemcpyAsync(dQin, job.Q + off, n * 4, cudaMemcpyHostToDevice, st));
+        FA2_CUDA(cudaMemcpyAsync(dKin, job.K + off, n * 4, cudaMemcpyHostToDevice, st));
+        FA2_CUDA(cudaMemcpyAsync(dVin, job.V + off, n * 4, cudaMemcpyHostToDevice, st));
+        if (job.mode == FA2_MODE_BACKWARD) {
+            FA2_CUDA(cudaMemcpyAsync(dO_, job.O_in + off, n * 4, cudaMemcpyHostToDevice, st));
+            FA2_CUDA(cudaMemcpyAsync(dL, job.LSE_in + offl, nl * 4, cudaMemcpyHostToDevice, st));
+        }
+        if (bwd) FA2_CUDA(cudaMemcpyAsync(ddO, job.dO + off, n * 4, cudaMemcpyHostToDevice, st));
+        FA2_CUDA(cudaEventRecord(e0, st));
+        if (job.mode == FA2_MODE_FORWARD)
+            rc = fa2_forward(dQin, dKin, dVin, dO_, dL, 1, count, job.S, job.D, job.precision, st);
+        else if (job.mode == FA2_MODE_BACKWARD)
+            rc = fa2_backward(dQin, dKin, dVin, dO_, ddO, dL, dQ_, dK_, dV_, 1, count, job.S, job.D, job.precision, st);
+        else
+            rc = fa2_forward_backward(dQin, dKin, dVin, ddO, dO_, dL, dQ_, dK_, dV_, 1, count, job.S, job.D,
+                                      job.precision, st);
+        if (rc) return rc;
+        FA2_CUDA(cudaEventRecord(e1, st));
+        if (fwd) {
+            FA2_CUDA(cudaMemcpyAsync(job.O + off, dO_, n * 4, cudaMemcpyDeviceToHost, st));
+            FA2_CUDA(cudaMemcpyAsync(job.LSE + offl, dL, nl * 4, cudaMemcpyDeviceToHost, st));
+        }
+        if (bwd) {
+            FA2_CUDA(cudaMemcpyAsync(job.dQ + off, dQ_, n * 4, cudaMemcpyDeviceToHost, st));
+            FA2_CUDA(cudaMemcpyAsync(job.dK + off, dK_, n * 4, cudaMemcpyDeviceToHost, st));
+            FA2_CUDA(cudaMemcpyAsync(job.dV + off, dV_, n * 4, cudaMemcpyDeviceToHost, st));
+        }
+        FA2_CUDA(cudaStreamSynchronize(st));
+        float ms = 0.f;
+        FA2_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        *ms_out = ms;
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        cudaStreamDestroy(st);
+        return FA2_OK;
+    };
+    int rc = run();
+    if (rc) *err_out = g_last_error;
+    return rc;
+}
+
+int host_dispatch(const HostJob& job, int n_gpus, float* kernel_ms) {
+    int rc = check_shape(job.B, job.H, job.S, job.D);
+    if (rc) return rc;
+    if ((rc = check_precision(job.precision))) return rc;
+    if (!job.Q || !job.K || !job.V) return fail(FA2_ERR_INVALID_ARGUMENT, "null input pointer");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        cudaGetLastError();
+        return fail(FA2_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+    }
+    if (n_gpus <= 0) n_gpus = 1;
+    if (n_gpus > ndev) return fail(FA2_ERR_INVALID_ARGUMENT, "n_gpus=%d but only %d device(s) visible", n_gpus, ndev);
+    const int BH = job.B * job.H;
+    if (n_gpus > BH) n_gpus = BH;
+    int prev_dev = 0;
+    cudaGetDevice(&prev_dev);
+    std::vector<std::thread> th;
+    std::vector<int> rcs(n_gpus, 0);
+    std::vector<float> ms(n_gpus, 0.f);
+    std::vector<std::string> errs(n_gpus);
+    for (int g = 0; g < n_gpus; ++g) {
+        int bh0 = 0, cnt = 0;
+        fa2_partition(BH, n_gpus, g, &bh0, &cnt);
+        th.emplace_back([&, g, bh0, cnt] { rcs[g] = host_worker(job, g, bh0, cnt, &ms[g], &errs[g]); });
+    }
+    for (auto& t : th) t.join();
+    cudaSetDevice(prev_dev);
+    float mx = 0.f;
+    for (int g = 0; g < n_gpus; ++g) {
+        if (rcs[g]) return fail(rcs[g], "device %d: %s", g, errs[g].c_str());
+        if (ms[g] > mx) mx = ms[g];
+    }
+    if (kernel_ms) *kernel_ms = mx;
+    return FA2_OK;
+}
+
+}  // namespace
+}  // namespace fa2
+
+using namespace fa2;
+
+extern "C" {
+
+int fa2_version(void) { return 100; }
+
+const char* fa2_last_error(void) { return g_last_error.c_str(); }
+
+size_t fa2_workspace_bytes(int B, int H, int S, int D, int mode) {
+    if (B <= 0 || H <= 0 || S <= 0 || (D != 32 && D != 64 && D != 128)) return 0;
+    return work_layout(static_cast<size_t>(B) * H * S, padded_head_dim(D), mode != FA2_MODE_FORWARD).total;
+}
+
+int fa2_partition(int BH, int n_parts, int part, int* bh0, int* count) {
+    if (BH < 0 || n_parts <= 0 || part < 0 || part >= n_parts || !bh0 || !count)
+        return fail(FA2_ERR_INVALID_ARGUMENT, "bad partition request BH=%d n_parts=%d part=%d", BH, n_parts, part);
+    const long long lo = static_cast<long long>(part) * BH / n_parts;
+    const long long hi = static_cast<long long>(part + 1) * BH / n_parts;
+    *bh0 = static_cast<int>(lo);
+    *count = static_cast<int>(hi - lo);
+    return FA2_OK;
+}
+
+int fa2_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int fa2_release_workspaces(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int prev = 0;
+    if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); return FA2_OK; }
+    for (int d = 0; d < kMaxDevices; ++d) {
+        for (Arena* a : {&g_work[d], &g_io[d]}) {
+            if (a->ptr) {
+                cudaSetDevice(d);
+                cudaDeviceSynchronize();
+                cudaFree(a->ptr);
+                a->ptr = nullptr;
+                a->bytes = 0;
+            }
+        }
+    }
+    cudaSetDevice(prev);
+    return FA2_OK;
+}
+
+int fa2_forward(const float* Q, const float* K, const float* V, float* O, float* LSE, int B, int H, int S, int D,
+                int precision, void* cuda_stream) {
+    if (!Q || !K || !V || !O || !LSE) return fail(FA2_ERR_INVALID_ARGUMENT, "null pointer argument");
+    Prepared pr;
+    int rc = prepare(&pr, B, H, S, D, precision, false);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    if ((rc = run_cast(pr, Q, K, V, st))) return rc;
+    return run_fwd_main(pr, O, LSE, st);
+}
+
+int fa2_backward(const float* Q, const float* K, const float* V, const float* O, const float* dO, const float* LSE,
+                 float* dQ, float* dK, float* dV, int B, int H, int S, int D, int precision, void* cuda_stream) {
+    if (!Q || !K || !V || !O || !dO || !LSE || !dQ || !dK || !dV)
+        return fail(FA2_ERR_INVALID_ARGUMENT, "null pointer argument");
+    Prepared pr;
+    int rc = prepare(&pr, B, H, S, D, precision, true);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    if ((rc = run_cast(pr, Q, K, V, st))) return rc;
+    return run_bwd_main(pr, O, dO, LSE, dQ, dK, dV, st);
+}
+
+int fa2_forward_backward(const float* Q, const float* K, const float* V, const float* dO, float* O, float* LSE,
+                         float* dQ, float* dK, float* dV, int B, int H, int S, int D, int precision,
+                         void* cuda_stream) {
+    if (!Q || !K || !V || !O || !dO || !LSE || !dQ || !dK || !dV)
+        return fail(FA2_ERR_INVALID_ARGUMENT, "null pointer argument");
+    Prepared pr;
+    int rc = prepare(&pr, B, H, S, D, precision, true);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    if ((rc = run_cast(pr, Q, K, V, st))) return rc;           // one 16-bit copy serves both passes
+    if ((rc = run_fwd_main(pr, O, LSE, st))) return rc;
+    return run_bwd_main(pr, O, dO, LSE, dQ, dK, dV, st);
+}
+
+int fa2_host_forward(const float* Q, const float* K, const float* V, float* O, float* LSE, int B, int H, int S,
+                     int D, int precision, int n_gpus, float* kernel_ms) {
+    if (!O || !LSE) return fail(FA2_ERR_INVALID_ARGUMENT, "null output pointer");
+    HostJob j{Q, K, V, nullptr, nullptr, nullptr, O, LSE, nullptr, nullptr, nullptr, B, H, S, D, precision,
+              FA2_MODE_FORWARD};
+    return host_dispatch(j, n_gpus, kernel_ms);
+}
+
+int fa2_host_backward(const float* Q, const float* K, const float* V, const float* O, const float* dO,
+                      const float* LSE, float* dQ, float* dK, float* dV, int B, int H, int S, int D, int precision,
+                      int n_gpus, float* kernel_ms) {
+    if (!O || !dO || !LSE || !dQ || !dK || !dV) return fail(FA2_ERR_INVALID_ARGUMENT, "null pointer argument");
+    HostJob j{Q, K, V, O, dO, LSE, nullptr, nullptr, dQ, dK, dV, B, H, S, D, precision, FA2_MODE_BACKWARD};
+    return host_dispatch(j, n_gpus, kernel_ms);
+}
+
+int fa2_host_forward_backward(const float* Q, const float* K, const float* V, const float* dO, float* O, float* LSE,
+                              float* dQ, float* dK, float* dV, int B, int H, int S, int D, int precision,
+                              int n_gpus, float* kernel_ms) {
+    if (!O || !dO || !LSE || !dQ || !dK || !dV) return fail(FA2_ERR_INVALID_ARGUMENT, "null pointer argument");
+    HostJob j{Q, K, V, nullptr, dO, nullptr, O, LSE, dQ, dK, dV, B, H, S, D, precision, FA2_MODE_FORWARD_BACKWARD};
+    return host_dispatch(j, n_gpus, kernel_ms);
+}
+
+}  // extern "C"

@@ -1,0 +1,53 @@
+// fa2_common.h -- internal declarations shared by the kernels and the C-ABI layer.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace fa2 {
+
+enum Precision { kOperandF16 = 0, kOperandBF16 = 1 };
+
+// 16-bit operand copies of the fp32 API tensors live in a per-device workspace as
+// [BH][S][DP] row-major, DP = padded head dim (64 or 128), zero padded when D < DP.
+inline int padded_head_dim(int D) { return D <= 64 ? 64 : 128; }
+
+struct FwdParams {
+    CUtensorMap tm_q;   // 16-bit [BH][S][DP], box {64, 128, 1}, 128B swizzle
+    CUtensorMap tm_k;
+    CUtensorMap tm_v;
+    float* O;           // fp32 [BH][S][D]
+    float* LSE;         // fp32 [BH][S] natural log
+    int BH, S, D;
+    float scale_log2;   // log2(e) / sqrt(D)
+    float scale;        // 1 / sqrt(D)
+    int bf16;
+};
+
+struct BwdParams {
+    CUtensorMap tm_q;    // 16-bit [BH][S][DP]
+    CUtensorMap tm_k;
+    CUtensorMap tm_v;
+    CUtensorMap tm_do;
+    const float* lse_log2;  // fp32 [BH][S]  LSE * log2(e)
+    const float* delta;     // fp32 [BH][S]  rowsum(dO * O)
+    float* dQ;              // fp32 [BH][S][D], zeroed by the pre-pass, reduce-added here
+    float* dK;
+    float* dV;
+    int BH, S, D;
+    float scale_log2;
+    float scale;
+    int bf16;
+};
+
+// launchers (each returns a cudaError_t from the launch)
+cudaError_t launch_cast_qkv(const float* Q, const float* K, const float* V, void* Qh, void* Kh, void* Vh,
+                            size_t rows, int D, int DP, int bf16, cudaStream_t st);
+cudaError_t launch_bwd_prepass(const float* O, const float* dO, const float* LSE, void* dOh, float* delta,
+                               float* lse_log2, float* dQ_zero, size_t rows, int D, int DP, int bf16,
+                               cudaStream_t st);
+cudaError_t launch_fwd(const FwdParams& p, cudaStream_t st);
+cudaError_t launch_bwd(const BwdParams& p, cudaStream_t st);
+
+}  // namespace fa2

@@ -1,0 +1,332 @@
+// fa2_fwd_sm100.cu -- FlashAttention-2 forward for sm_100a (replaces the reference's
+// flash_attention2_forward_kernel, kernels/kernel_fa2_optimized.cu:19-347).
+//
+// One CTA owns 256 query rows of one (batch, head) slab as two 128-row tiles and walks the
+// 128-row KV tiles.  Roles (10 warps):
+//   warps 0-3  softmax for Q tile 0   (thread == one query row, TMEM lane == row)
+//   warps 4-7  softmax for Q tile 1
+//   warp  8    MMA issuer (one thread issues tcgen05.mma; the warp also owns TMEM alloc/free)
+//   warp  9    TMA producer (Q once, K/V double-buffered through shared memory)
+// S_t = Q_t K_j^T and O_t += P_t V_j run as tcgen05.mma (kind::f16, fp32 accumulate) with
+// S and O in TMEM; P is written back to TMEM over S as 16-bit and fed to the second MMA as
+// the A operand straight from TMEM.  The online softmax keeps max / sum per thread in
+// registers, works in the exp2 domain and only rescales O when the running max moved by
+// more than 2^8 (warp-uniform decision), then normalises and stores fp32 O and natural-log
+// LSE = ln(l) + m  (reference epilogue: kernel_fa2_optimized.cu:327-346).
+#include "fa2_common.h"
+#include "ptx.cuh"
+
+namespace fa2 {
+
+namespace {
+
+constexpr int BM = 128;         // query rows per tile
+constexpr int BN = 128;         // kv rows per tile
+constexpr int KV_STAGES = 2;
+constexpr int NUM_THREADS = 320;
+constexpr int MMA_WARP = 8;
+constexpr int TMA_WARP = 9;
+constexpr float RESCALE_THRESHOLD = 8.0f;   // log2 units
+
+template <int DP>
+struct FwdSmem {
+    static constexpr int TILE_BYTES = BM * DP * 2;          // one 128-row 16-bit tile
+    static constexpr int ATOM_BYTES = BM * 128;              // one [128][64] swizzle-atom column
+    static constexpr int OFF_Q = 0;                           // 2 tiles
+    static constexpr int OFF_K = OFF_Q + 2 * TILE_BYTES;      // KV_STAGES tiles
+    static constexpr int OFF_V = OFF_K + KV_STAGES * TILE_BYTES;
+    static constexpr int OFF_BAR = OFF_V + KV_STAGES * TILE_BYTES;
+    static constexpr int NUM_BARS = 2 + 4 * KV_STAGES + 2 + 2 + 2;
+    static constexpr int OFF_TMEM_PTR = OFF_BAR + NUM_BARS * 8;
+    static constexpr int BYTES = OFF_TMEM_PTR + 16;
+    static constexpr int ALLOC = BYTES + 1024;                // slack for manual 1024-B alignment
+};
+
+template <int DP>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+fa2_fwd_kernel(const __grid_constant__ FwdParams p) {
+    using L = FwdSmem<DP>;
+    constexpr int KSTEPS_QK = DP / 16;          // UMMA K = 16 for 16-bit operands
+    constexpr int KSTEPS_PV = BN / 16;
+    constexpr uint32_t TMEM_COLS = 512;
+    constexpr uint32_t COL_S0 = 0, COL_S1 = 128, COL_O0 = 256, COL_O1 = 256 + DP;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
+    uint64_t* q_full = bars;                       // [2]
+    uint64_t* k_full = bars + 2;                   // [KV_STAGES]
+    uint64_t* k_empty = k_full + KV_STAGES;
+    uint64_t* v_full = k_empty + KV_STAGES;
+    uint64_t* v_empty = v_full + KV_STAGES;
+    uint64_t* s_full = v_empty + KV_STAGES;        // [2]
+    uint64_t* p_full = s_full + 2;                 // [2]
+    uint64_t* o_full = p_full + 2;                 // [2]
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + L::OFF_TMEM_PTR);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    const int q_blocks = (p.S + 2 * BM - 1) / (2 * BM);
+    const int bh = blockIdx.x / q_blocks;
+    const int q_row0 = (blockIdx.x % q_blocks) * (2 * BM);
+    const int n_qt = (q_row0 + BM < p.S) ? 2 : 1;            // second tile may be fully out of range
+    const int n_kv = (p.S + BN - 1) / BN;
+
+    if (warp == TMA_WARP && lane == 0) {
+        tma_prefetch_desc(&p.tm_q);
+        tma_prefetch_desc(&p.tm_k);
+        tma_prefetch_desc(&p.tm_v);
+    }
+    if (warp == MMA_WARP) {
+        if (lane == 0) {
+            for (int i = 0; i < 2; ++i) {
+                mbar_init(&q_full[i], 1);
+                mbar_init(&s_full[i], 1);
+                mbar_init(&p_full[i], 4);       // one arrive per softmax warp
+                mbar_init(&o_full[i], 1);
+            }
+            for (int i = 0; i < KV_STAGES; ++i) {
+                mbar_init(&k_full[i], 1);
+                mbar_init(&k_empty[i], 1);
+                mbar_init(&v_full[i], 1);
+                mbar_init(&v_empty[i], 1);
+            }
+            fence_mbar_init();
+        }
+        __syncwarp();
+        tmem_alloc(tmem_holder, TMEM_COLS);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    if (warp == TMA_WARP) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            for (int t = 0; t < n_qt; ++t) {
+                mbar_expect_tx(&q_full[t], L::TILE_BYTES);
+                for (int a = 0; a < DP / 64; ++a)
+                    tma_load_3d(smem + L::OFF_Q + t * L::TILE_BYTES + a * L::ATOM_BYTES, &p.tm_q, &q_full[t],
+                                a * 64, q_row0 + t * BM, bh);
+            }
+            for (int j = 0; j < n_kv; ++j) {
+                const int s = j % KV_STAGES;
+                const uint32_t ph = (j / KV_STAGES) & 1;
+                mbar_wait(&k_empty[s], ph ^ 1);
+                mbar_expect_tx(&k_full[s], L::TILE_BYTES);
+                for (int a = 0; a < DP / 64; ++a)
+                    tma_load_3d(smem + L::OFF_K + s * L::TILE_BYTES + a * L::ATOM_BYTES, &p.tm_k, &k_full[s],
+                                a * 64, j * BN, bh);
+                mbar_wait(&v_empty[s], ph ^ 1);
+                mbar_expect_tx(&v_full[s], L::TILE_BYTES);
+                for (int a = 0; a < DP / 64; ++a)
+                    tma_load_3d(smem + L::OFF_V + s * L::TILE_BYTES + a * L::ATOM_BYTES, &p.tm_v, &v_full[s],
+                                a * 64, j * BN, bh);
+            }
+        }
+    } else if (warp == MMA_WARP) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc_qk = umma_idesc_f16(BM, BN, 0, 0, p.bf16);
+            const uint32_t idesc_pv = umma_idesc_f16(BM, DP, 0, 1, p.bf16);
+            const uint32_t q_addr = smem_u32(smem + L::OFF_Q);
+            const uint32_t k_addr = smem_u32(smem + L::OFF_K);
+            const uint32_t v_addr = smem_u32(smem + L::OFF_V);
+            const uint32_t col_s[2] = {COL_S0, COL_S1};
+            const uint32_t col_o[2] = {COL_O0, COL_O1};
+
+            auto issue_qk = [&](int t, int s) {
+                // S_t = Q_t K^T : A, B both K-major, DP/64 swizzle atoms, 4 K-steps of 32 B per atom
+#pragma unroll
+                for (int k = 0; k < KSTEPS_QK; ++k) {
+                    const uint32_t off = (k >> 2) * L::ATOM_BYTES + (k & 3) * 32;
+                    umma_ss(tmem_base + col_s[t],
+                            umma_smem_desc(q_addr + t * L::TILE_BYTES + off, 16, 1024),
+                            umma_smem_desc(k_addr + s * L::TILE_BYTES + off, 16, 1024), idesc_qk, k > 0);
+                }
+            };
+            auto issue_pv = [&](int t, int s, bool first) {
+                // O_t += P_t V : A = P from TMEM (8 columns per K-step), B = V MN-major
+#pragma unroll
+                for (int k = 0; k < KSTEPS_PV; ++k) {
+                    umma_ts(tmem_base + col_o[t], tmem_base + col_s[t] + k * 8,
+                            umma_smem_desc(v_addr + s * L::TILE_BYTES + k * 2048, L::ATOM_BYTES, 1024), idesc_pv,
+                            (!first || k > 0) ? 1u : 0u);
+                }
+            };
+
+            mbar_wait(&k_full[0], 0);
+            for (int t = 0; t < n_qt; ++t) {
+                mbar_wait(&q_full[t], 0);
+                tc_fence_after();
+                issue_qk(t, 0);
+                umma_commit(&s_full[t]);
+            }
+            umma_commit(&k_empty[0]);   // K(0) is free once every S(0) has been computed
+            for (int j = 0; j < n_kv; ++j) {
+                const int s = j % KV_STAGES;
+                const uint32_t ph = (j / KV_STAGES) & 1;
+                const int s1 = (j + 1) % KV_STAGES;
+                const uint32_t ph1 = ((j + 1) / KV_STAGES) & 1;
+                mbar_wait(&v_full[s], ph);
+                for (int t = 0; t < n_qt; ++t) {
+                    mbar_wait(&p_full[t], j & 1);
+                    tc_fence_after();
+                    issue_pv(t, s, j == 0);
+                    if (t == n_qt - 1) umma_commit(&v_empty[s]);
+                    if (j + 1 < n_kv) {
+                        if (t == 0) {
+                            mbar_wait(&k_full[s1], ph1);
+                            tc_fence_after();
+                        }
+                        issue_qk(t, s1);
+                        umma_commit(&s_full[t]);
+                        if (t == n_qt - 1) umma_commit(&k_empty[s1]);
+                    } else {
+                        umma_commit(&o_full[t]);
+                    }
+                }
+            }
+        }
+    } else if (warp < 4 * n_qt) {
+        // ------------------------------------------------------------------ softmax + epilogue
+        const int t = warp >> 2;
+        const int row_in_tile = (warp & 3) * 32 + lane;
+        const int q_row = q_row0 + t * BM + row_in_tile;
+        const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
+        const uint32_t t_s = tmem_base + lane_addr + (t == 0 ? COL_S0 : COL_S1);
+        const uint32_t t_o = tmem_base + lane_addr + (t == 0 ? COL_O0 : COL_O1);
+        const float c2 = p.scale_log2;
+
+        float m_ref = -INFINITY;   // running reference max (raw score units)
+        float l_run = 0.0f;
+
+        for (int j = 0; j < n_kv; ++j) {
+            mbar_wait(&s_full[t], j & 1);
+            tc_fence_after();
+
+            uint32_t sr[4][32];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) tmem_ld32(t_s + c * 32, sr[c]);
+            tmem_wait_ld();
+
+            const int valid = p.S - j * BN;     // columns >= valid are padding in the last tile
+            if (valid < BN) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (c * 32 + i >= valid) sr[c][i] = __float_as_uint(-INFINITY);
+            }
+
+            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                mx0 = fmaxf(mx0, __uint_as_float(sr[0][i]));
+                mx1 = fmaxf(mx1, __uint_as_float(sr[1][i]));
+                mx2 = fmaxf(mx2, __uint_as_float(sr[2][i]));
+                mx3 = fmaxf(mx3, __uint_as_float(sr[3][i]));
+            }
+            const float m_new = fmaxf(fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)), m_ref);
+
+            if (j == 0) {
+                m_ref = m_new;
+            } else {
+                const bool need = (m_new - m_ref) * c2 > RESCALE_THRESHOLD;
+                if (__any_sync(0xffffffffu, need)) {
+                    // S(j) complete implies O += P V (j-1) complete (commits are ordered), so O is quiescent.
+                    const float alpha = ex2_approx((m_ref - m_new) * c2);
+                    m_ref = m_new;
+                    l_run *= alpha;
+#pragma unroll
+                    for (int c = 0; c < DP / 32; ++c) {
+                        uint32_t orr[32];
+                        tmem_ld32(t_o + c * 32, orr);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) orr[i] = __float_as_uint(__uint_as_float(orr[i]) * alpha);
+                        tmem_st32(t_o + c * 32, orr);
+                    }
+                }
+            }
+
+            // P = 2^(S*c2 - m*c2), packed to 16 bit and written over S (all of S is already in registers)
+            const float neg_m = -m_ref * c2;
+            float lsum[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t pk[16];
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    const float e0 = ex2_approx(fmaf(__uint_as_float(sr[c][i]), c2, neg_m));
+                    const float e1 = ex2_approx(fmaf(__uint_as_float(sr[c][i + 1]), c2, neg_m));
+                    lsum[c] += e0 + e1;
+                    pk[i >> 1] = p.bf16 ? pack_bf16x2(e0, e1) : pack_half2(e0, e1);
+                }
+                tmem_st16(t_s + c * 16, pk);
+            }
+            l_run += (lsum[0] + lsum[1]) + (lsum[2] + lsum[3]);
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_full[t]);
+        }
+
+        // epilogue: O / l -> fp32 global, LSE = ln(l) + m / sqrt(D)
+        mbar_wait(&o_full[t], 0);
+        tc_fence_after();
+        const float inv_l = 1.0f / l_run;
+        const bool row_ok = q_row < p.S;
+        float* o_row = p.O + (static_cast<size_t>(bh) * p.S + (row_ok ? q_row : 0)) * p.D;
+#pragma unroll
+        for (int c = 0; c < DP / 32; ++c) {
+            uint32_t orr[32];
+            tmem_ld32(t_o + c * 32, orr);
+            tmem_wait_ld();
+            if (row_ok && c * 32 < p.D) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    float4 v4;
+                    v4.x = __uint_as_float(orr[i]) * inv_l;
+                    v4.y = __uint_as_float(orr[i + 1]) * inv_l;
+                    v4.z = __uint_as_float(orr[i + 2]) * inv_l;
+                    v4.w = __uint_as_float(orr[i + 3]) * inv_l;
+                    *reinterpret_cast<float4*>(o_row + c * 32 + i) = v4;
+                }
+            }
+        }
+        if (row_ok)
+            p.LSE[static_cast<size_t>(bh) * p.S + q_row] = m_ref * p.scale + logf(l_run);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == MMA_WARP) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_fwd(const FwdParams& p, cudaStream_t st) {
+    const int DP = padded_head_dim(p.D);
+    const int q_blocks = (p.S + 2 * BM - 1) / (2 * BM);
+    const dim3 grid(static_cast<unsigned>(p.BH) * q_blocks);
+    cudaError_t e;
+    if (DP == 64) {
+        e = cudaFuncSetAttribute(fa2_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem<64>::ALLOC);
+        if (e != cudaSuccess) return e;
+        fa2_fwd_kernel<64><<<grid, NUM_THREADS, FwdSmem<64>::ALLOC, st>>>(p);
+    } else {
+        e = cudaFuncSetAttribute(fa2_fwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 FwdSmem<128>::ALLOC);
+        if (e != cudaSuccess) return e;
+        fa2_fwd_kernel<128><<<grid, NUM_THREADS, FwdSmem<128>::ALLOC, st>>>(p);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace fa2

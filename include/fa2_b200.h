@@ -1,0 +1,103 @@
+/*
+ * fa2_b200.h -- C ABI of libfa2_b200.so, the B200-native (sm_100a) drop-in for the
+ * FlashAttention-2 forward/backward path of detker/CUDA-Flash-Attention.
+ *
+ * Plain pointers and sizes only; no C++/torch types; no exit() -- every entry point returns
+ * 0 on success or an FA2_ERR_* code, with a message available from fa2_last_error().
+ * Tensors are fp32, row-major contiguous [B,H,S,D]; logsumexp (natural log) is [B,H,S]
+ * (reference layout: src/main.cpp:27-38, kernels/kernel_fa2_optimized.cu:56-58,:340-343).
+ * Supported head dims: 32, 64, 128 (the reference dispatches 32 and 64 only,
+ * include/dispatcher.h:226-227).  There is no CPU fallback: without a B200 the compute
+ * entry points fail with FA2_ERR_CUDA.
+ */
+#ifndef FA2_B200_H
+#define FA2_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FA2_OK 0
+#define FA2_ERR_INVALID_ARGUMENT 1   /* null pointer, non-positive dim, unsupported head dim */
+#define FA2_ERR_CUDA 2               /* a CUDA runtime/driver call failed (see fa2_last_error) */
+#define FA2_ERR_UNSUPPORTED 3        /* valid request this build cannot serve (e.g. method fa1/naive) */
+#define FA2_ERR_IO 4                 /* CLI layer: missing / short .bin file */
+
+/* <SHM_precision> of the reference CLI (include/enum_types.h:15-18).  Both values run
+ * 16-bit tensor-core operands with fp32 accumulation; FP32 selects fp16 operands with the
+ * tighter tolerance contract, FP16 is the reference's "fp16 shared-memory mode". */
+#define FA2_PRECISION_FP16 0
+#define FA2_PRECISION_FP32 1
+#define FA2_PRECISION_BF16 2         /* bf16 operands (wider range, LSE error ~1e-3) */
+
+/* mode for fa2_workspace_bytes (include/enum_types.h:9-13) */
+#define FA2_MODE_FORWARD 0
+#define FA2_MODE_BACKWARD 1
+#define FA2_MODE_FORWARD_BACKWARD 2
+
+int fa2_version(void);
+/* Thread-local text of the last failure on the calling thread ("" if none). */
+const char* fa2_last_error(void);
+/* Device scratch (16-bit operand copies, D_i, log2-domain LSE) the library keeps per device. */
+size_t fa2_workspace_bytes(int B, int H, int S, int D, int mode);
+
+/* ---------------------------------------------------------------------------------------
+ * Device-pointer entry points.  Replace the reference's kernel-level ABI
+ *   flash_attention2_forward_kernel_wrapper   kernels/kernel_fa2_optimized.cu:428-444
+ *   D_computation_reduction_kernel_wrapper    kernels/f-attn2-backward.cu:514-528
+ *   flash_attention2_backward_kernel_wrapper  kernels/f-attn2-backward.cu:491-512
+ * as called by the harness (test_flash_attention2.py:278-289, :504-535).  All pointers are
+ * device pointers on the current device, caller-owned.  Asynchronous on `cuda_stream`
+ * (a cudaStream_t, NULL = default stream).  fa2_backward computes D_i = rowsum(dO*O) and
+ * zero-fills dQ itself (the reference needs a separate launch and three fill(0)s).
+ * ------------------------------------------------------------------------------------- */
+int fa2_forward(const float* Q, const float* K, const float* V, float* O, float* LSE,
+                int B, int H, int S, int D, int precision, void* cuda_stream);
+
+int fa2_backward(const float* Q, const float* K, const float* V, const float* O, const float* dO,
+                 const float* LSE, float* dQ, float* dK, float* dV,
+                 int B, int H, int S, int D, int precision, void* cuda_stream);
+
+/* forward then backward without the reference's device->host->device round trip of O/LSE
+ * (include/dispatcher.h:91-104) and with one shared 16-bit copy of Q, K, V. */
+int fa2_forward_backward(const float* Q, const float* K, const float* V, const float* dO,
+                         float* O, float* LSE, float* dQ, float* dK, float* dV,
+                         int B, int H, int S, int D, int precision, void* cuda_stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Host-pointer entry points.  Replace host_flash_attention2_forward<D> / _backward<D>
+ * (+ _fp16 twins; kernels/f-attn2.cuh:13-71, called from include/dispatcher.h:24-27,:66-71).
+ * NOTE the argument order here is (B, H, S, D); the reference templates take (B, S, H).
+ * Pointers are host memory, caller-owned; the call is synchronous.  The batch*head slabs are
+ * split over the first n_gpus visible devices (n_gpus <= 0: use one); each device's share is
+ * independent so there is no collective.  *kernel_ms (optional) receives the max over devices
+ * of the device-side time of everything between fp32 inputs and fp32 outputs in device
+ * memory (what the reference's TimerGPU measures, include/timer.h:50-64, plus our pre-passes).
+ * ------------------------------------------------------------------------------------- */
+int fa2_host_forward(const float* Q, const float* K, const float* V, float* O, float* LSE,
+                     int B, int H, int S, int D, int precision, int n_gpus, float* kernel_ms);
+
+int fa2_host_backward(const float* Q, const float* K, const float* V, const float* O, const float* dO,
+                      const float* LSE, float* dQ, float* dK, float* dV,
+                      int B, int H, int S, int D, int precision, int n_gpus, float* kernel_ms);
+
+int fa2_host_forward_backward(const float* Q, const float* K, const float* V, const float* dO,
+                              float* O, float* LSE, float* dQ, float* dK, float* dV,
+                              int B, int H, int S, int D, int precision, int n_gpus, float* kernel_ms);
+
+/* The host-side partitioner: slab range [*bh0, *bh0 + *count) of part `part` out of `n_parts`
+ * over BH = B*H independent (batch, head) slabs.  Pure arithmetic, no GPU needed. */
+int fa2_partition(int BH, int n_parts, int part, int* bh0, int* count);
+
+/* Number of CUDA devices visible to the library (0 without a GPU; never fails). */
+int fa2_device_count(void);
+
+/* Release every per-device workspace the library holds. */
+int fa2_release_workspaces(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FA2_B200_H */
