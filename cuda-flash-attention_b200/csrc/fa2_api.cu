@@ -73,6 +73,21 @@ int make_tmap_16(CUtensorMap* tm, void* base, int BH, int S, int DP, int box_row
     return FA2_OK;
 }
 
+// fp32 [BH][S][D] tensor addressed by the dQ reduce-add: box {32 cols, 128 rows, 1 slab}, 128-byte swizzle.
+int make_tmap_f32(CUtensorMap* tm, void* base, int BH, int S, int D) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return fail(FA2_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    cuuint64_t dims[3] = {static_cast<cuuint64_t>(D), static_cast<cuuint64_t>(S), static_cast<cuuint64_t>(BH)};
+    cuuint64_t strides[2] = {static_cast<cuuint64_t>(D) * 4, static_cast<cuuint64_t>(S) * D * 4};
+    cuuint32_t box[3] = {32, 128, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(FA2_ERR_CUDA, "cuTensorMapEncodeTiled(fp32) failed with CUresult %d", (int)r);
+    return FA2_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // per-device arenas (grown on demand, kept until fa2_release_workspaces)
 // ------------------------------------------------------------------------------------------
@@ -196,6 +211,7 @@ int run_bwd_main(const Prepared& pr, const float* O, const float* dO, const floa
     if ((rc = make_tmap_16(&p.tm_k, pr.work + pr.wl.off_k, pr.BH, pr.S, pr.DP, 128, pr.bf16))) return rc;
     if ((rc = make_tmap_16(&p.tm_v, pr.work + pr.wl.off_v, pr.BH, pr.S, pr.DP, 128, pr.bf16))) return rc;
     if ((rc = make_tmap_16(&p.tm_do, pr.work + pr.wl.off_do, pr.BH, pr.S, pr.DP, 128, pr.bf16))) return rc;
+    if ((rc = make_tmap_f32(&p.tm_dq, dQ, pr.BH, pr.S, pr.D))) return rc;
     p.lse_log2 = lse2; p.delta = delta; p.dQ = dQ; p.dK = dK; p.dV = dV;
     p.BH = pr.BH; p.S = pr.S; p.D = pr.D; p.scale = pr.scale; p.scale_log2 = pr.scale_log2; p.bf16 = pr.bf16;
     FA2_CUDA(launch_bwd(p, st));
