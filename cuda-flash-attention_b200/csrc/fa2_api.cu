@@ -181,7 +181,22 @@ int prepare(Prepared* pr, int B, int H, int S, int D, int precision, bool backwa
     return FA2_OK;
 }
 
+// optional per-kernel timing (fa2_profile_enable / fa2_profile_read)
+bool g_profile = false;
+struct ProfSpan { int kind; cudaEvent_t a, b; };
+std::vector<ProfSpan> g_spans;
+struct ProfScope {
+    int kind; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr; bool on;
+    ProfScope(int k, cudaStream_t s) : kind(k), st(s), on(g_profile) {
+        if (on) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, st); }
+    }
+    ~ProfScope() {
+        if (on) { cudaEventRecord(b, st); g_spans.push_back({kind, a, b}); }
+    }
+};
+
 int run_cast(const Prepared& pr, const float* Q, const float* K, const float* V, cudaStream_t st) {
+    ProfScope prof(0, st);
     FA2_CUDA(launch_cast_qkv(Q, K, V, pr.work + pr.wl.off_q, pr.work + pr.wl.off_k, pr.work + pr.wl.off_v, pr.rows,
                              pr.D, pr.DP, pr.bf16, st));
     return FA2_OK;
@@ -195,6 +210,7 @@ int run_fwd_main(const Prepared& pr, float* O, float* LSE, cudaStream_t st) {
     if ((rc = make_tmap_16(&p.tm_v, pr.work + pr.wl.off_v, pr.BH, pr.S, pr.DP, 128, pr.bf16))) return rc;
     p.O = O; p.LSE = LSE; p.BH = pr.BH; p.S = pr.S; p.D = pr.D;
     p.scale = pr.scale; p.scale_log2 = pr.scale_log2; p.bf16 = pr.bf16;
+    ProfScope prof(1, st);
     FA2_CUDA(launch_fwd(p, st));
     return FA2_OK;
 }
@@ -203,8 +219,11 @@ int run_bwd_main(const Prepared& pr, const float* O, const float* dO, const floa
                  float* dV, cudaStream_t st) {
     float* delta = reinterpret_cast<float*>(pr.work + pr.wl.off_delta);
     float* lse2 = reinterpret_cast<float*>(pr.work + pr.wl.off_lse2);
+    {
+    ProfScope prof(2, st);
     FA2_CUDA(launch_bwd_prepass(O, dO, LSE, pr.work + pr.wl.off_do, delta, lse2, dQ, pr.rows, pr.D, pr.DP, pr.bf16,
                                 st));
+    }
     BwdParams p{};
     int rc;
     if ((rc = make_tmap_16(&p.tm_q, pr.work + pr.wl.off_q, pr.BH, pr.S, pr.DP, 128, pr.bf16))) return rc;
@@ -214,6 +233,7 @@ int run_bwd_main(const Prepared& pr, const float* O, const float* dO, const floa
     if ((rc = make_tmap_f32(&p.tm_dq, dQ, pr.BH, pr.S, pr.D))) return rc;
     p.lse_log2 = lse2; p.delta = delta; p.dQ = dQ; p.dK = dK; p.dV = dV;
     p.BH = pr.BH; p.S = pr.S; p.D = pr.D; p.scale = pr.scale; p.scale_log2 = pr.scale_log2; p.bf16 = pr.bf16;
+    ProfScope prof(3, st);
     FA2_CUDA(launch_bwd(p, st));
     return FA2_OK;
 }
@@ -323,7 +343,8 @@ int host_dispatch(const HostJob& job, int n_gpus, float* kernel_ms) {
     for (int g = 0; g < n_gpus; ++g) {
         int bh0 = 0, cnt = 0;
         fa2_partition(BH, n_gpus, g, &bh0, &cnt);
-        th.emplace_back([&, g, bh0, cnt] { rcs[g] = host_worker(job, g, bh0, cnt, &ms[g], &errs[g]); });
+        const int dev = (n_gpus == 1) ? prev_dev : g;      // one GPU: the caller's current device
+        th.emplace_back([&, g, dev, bh0, cnt] { rcs[g] = host_worker(job, dev, bh0, cnt, &ms[g], &errs[g]); });
     }
     for (auto& t : th) t.join();
     cudaSetDevice(prev_dev);
@@ -369,6 +390,58 @@ int fa2_device_count(void) {
         return 0;
     }
     return n;
+}
+
+namespace {
+std::mutex g_host_mu;
+std::vector<void*> g_pinned;   // pointers that came from cudaMallocHost
+}
+
+void* fa2_host_alloc(size_t bytes) {
+    if (bytes == 0) bytes = 1;
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) == cudaSuccess && p) {
+        std::lock_guard<std::mutex> lk(g_host_mu);
+        g_pinned.push_back(p);
+        return p;
+    }
+    cudaGetLastError();
+    p = malloc(bytes);
+    if (!p) fail(FA2_ERR_INVALID_ARGUMENT, "host allocation of %zu bytes failed", bytes);
+    return p;
+}
+
+void fa2_host_free(void* p) {
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> lk(g_host_mu);
+        for (size_t i = 0; i < g_pinned.size(); ++i)
+            if (g_pinned[i] == p) {
+                g_pinned.erase(g_pinned.begin() + i);
+                cudaFreeHost(p);
+                return;
+            }
+    }
+    free(p);
+}
+
+int fa2_profile_enable(int on) {
+    g_profile = on != 0;
+    return FA2_OK;
+}
+
+int fa2_profile_read(float* ms, int* launches) {
+    for (const ProfSpan& sp : g_spans) {
+        float t = 0.f;
+        if (cudaEventSynchronize(sp.b) == cudaSuccess && cudaEventElapsedTime(&t, sp.a, sp.b) == cudaSuccess) {
+            if (ms) ms[sp.kind] += t;
+            if (launches) launches[sp.kind] += 1;
+        }
+        cudaEventDestroy(sp.a);
+        cudaEventDestroy(sp.b);
+    }
+    g_spans.clear();
+    return FA2_OK;
 }
 
 int fa2_release_workspaces(void) {

@@ -33,6 +33,10 @@ SIGNATURES = {
     "fa2_partition": (_i, [_i, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(_i)]),
     "fa2_device_count": (_i, []),
     "fa2_release_workspaces": (_i, []),
+    "fa2_profile_enable": (_i, [_i]),
+    "fa2_profile_read": (_i, [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_i)]),
+    "fa2_host_alloc": (ctypes.c_void_p, [ctypes.c_size_t]),
+    "fa2_host_free": (None, [ctypes.c_void_p]),
 }
 
 _lib = None

@@ -71,7 +71,7 @@ int fa2_forward_backward(const float* Q, const float* K, const float* V, const f
  * (+ _fp16 twins; kernels/f-attn2.cuh:13-71, called from include/dispatcher.h:24-27,:66-71).
  * NOTE the argument order here is (B, H, S, D); the reference templates take (B, S, H).
  * Pointers are host memory, caller-owned; the call is synchronous.  The batch*head slabs are
- * split over the first n_gpus visible devices (n_gpus <= 0: use one); each device's share is
+ * split over devices 0..n_gpus-1 (n_gpus <= 1: the caller's current device only); each device's share is
  * independent so there is no collective.  *kernel_ms (optional) receives the max over devices
  * of the device-side time of everything between fp32 inputs and fp32 outputs in device
  * memory (what the reference's TimerGPU measures, include/timer.h:50-64, plus our pre-passes).
@@ -93,6 +93,20 @@ int fa2_partition(int BH, int n_parts, int part, int* bh0, int* count);
 
 /* Number of CUDA devices visible to the library (0 without a GPU; never fails). */
 int fa2_device_count(void);
+
+/* Page-locked host memory for the host-pointer entry points and the CLI (falls back to malloc
+ * when no CUDA device is present so that argument/IO errors are still reported on a CPU box).
+ * Free with fa2_host_free. */
+void* fa2_host_alloc(size_t bytes);
+void fa2_host_free(void* p);
+
+/* Per-kernel device timing for bench.py's roofline leg.  When enabled, the device-pointer entry
+ * points bracket each of their kernels with cudaEvents on the launch stream.  fa2_profile_read
+ * waits for the recorded events, ADDS the elapsed milliseconds since the previous read into
+ * ms[4] = {cast pre-pass, forward kernel, backward pre-pass, backward kernel} and the number of
+ * launches into launches[4], then clears the record.  Not thread-safe; off by default. */
+int fa2_profile_enable(int on);
+int fa2_profile_read(float* ms, int* launches);
 
 /* Release every per-device workspace the library holds. */
 int fa2_release_workspaces(void);

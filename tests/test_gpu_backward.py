@@ -1,0 +1,116 @@
+"""-m gpu parity: the sm_100a backward (and fused forward_backward) through the C ABI."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+@pytest.fixture(scope="module")
+def U():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("-m gpu tests need a CUDA device; the FA2 path has no CPU fallback")
+    from tests import gpu_util
+    return gpu_util
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_backward_vs_golden_harness_mode(U, path):
+    """Harness '--mode backward' (test_flash_attention2.py:917-928): reference O and LSE in, dO = ones."""
+    z = np.load(path)
+    dQ, dK, dV = U.gpu_backward(z["Q"], z["K"], z["V"], z["O"], np.ones_like(z["O"]), z["LSE"])
+    got = np.concatenate([dQ.ravel(), dK.ravel(), dV.ravel()])
+    want = np.concatenate([z["dQ"].ravel(), z["dK"].ravel(), z["dV"].ravel()])
+    assert np.isfinite(got).all()
+    assert U.maxerr(got, want) < U.TOL_GRAD
+
+
+@pytest.mark.parametrize("path", GOLDEN[:3], ids=[os.path.basename(p)[:-4] for p in GOLDEN[:3]])
+def test_forward_backward_vs_golden_both_mode(U, path):
+    """Harness '--mode both' (:608-728): our own O/LSE feed the backward."""
+    import torch
+    import fa2_b200
+    z = np.load(path)
+    outs = fa2_b200.forward_backward(U.dev(z["Q"]), U.dev(z["K"]), U.dev(z["V"]), U.dev(np.ones_like(z["Q"])))
+    torch.cuda.synchronize()
+    O, L, dQ, dK, dV = (U.host(t) for t in outs)
+    assert U.maxerr(O, z["O"]) < U.TOL_O and U.maxerr(L, z["LSE"]) < U.TOL_LSE
+    for a, n in ((dQ, "dQ"), (dK, "dK"), (dV, "dV")):
+        assert U.maxerr(a, z[n]) < U.TOL_GRAD, n
+
+
+SHAPES = [
+    (1, 1, 128, 64), (2, 4, 256, 64), (2, 2, 512, 64), (1, 2, 1024, 64),
+    (2, 3, 100, 64), (2, 3, 32, 64), (1, 2, 129, 64), (1, 2, 257, 64), (1, 1, 1000, 64),
+    (1, 2, 1, 64), (1, 1, 383, 128), (1, 2, 512, 128), (2, 2, 256, 32), (1, 1, 77, 32), (1, 1, 2048, 128),
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=["B%d_H%d_S%d_D%d" % s for s in SHAPES])
+def test_backward_vs_fp64_truth_random_dO(U, shape):
+    Q, K, V, dO = U.randn_case(shape, seed=21)
+    tO, tL, tdQ, tdK, tdV = U.orc.attention_fp64(Q, K, V, dO)
+    dQ, dK, dV = U.gpu_backward(Q, K, V, tO.astype(np.float32), dO, tL.astype(np.float32))
+    assert U.maxerr(dQ, tdQ) < U.TOL_GRAD
+    assert U.maxerr(dK, tdK) < U.TOL_GRAD
+    assert U.maxerr(dV, tdV) < U.TOL_GRAD
+    if shape[2] <= 257:                       # C restatement of the reference kernels on the same inputs
+        cO, cL = U.orc.forward(Q, K, V)
+        cdQ, cdK, cdV = U.orc.backward(Q, K, V, cO, dO, cL)
+        assert max(U.maxerr(dQ, cdQ), U.maxerr(dK, cdK), U.maxerr(dV, cdV)) < U.TOL_GRAD
+
+
+def test_backward_is_rerunnable_dq_zeroed_internally(U):
+    """The reference needs dQ memset before every launch (test :546-548); ours zero-fills itself."""
+    import torch
+    import fa2_b200
+    Q, K, V, dO = U.randn_case((1, 2, 300, 64), seed=4)
+    tO, tL, tdQ, _, _ = U.orc.attention_fp64(Q, K, V, dO)
+    q, k, v, o, g, l = (U.dev(x) for x in (Q, K, V, tO, dO, tL))
+    out = tuple(torch.full_like(q, 123.0) for _ in range(3))
+    for _ in range(3):
+        fa2_b200.backward(q, k, v, o, g, l, out=out)
+    torch.cuda.synchronize()
+    assert U.maxerr(U.host(out[0]), tdQ) < U.TOL_GRAD
+
+
+def test_backward_properties_full_size(U):
+    """Larger sizes: linearity in dO, and an fp64 spot check of one head."""
+    import torch
+    import fa2_b200
+    for (B, H, S, D) in [(2, 8, 512, 64), (1, 2, 4096, 128)]:
+        g = torch.Generator(device="cuda").manual_seed(2)
+        Q, K, V, G1, G2 = (torch.randn(B, H, S, D, device="cuda", generator=g) for _ in range(5))
+        O, L = fa2_b200.forward(Q, K, V)
+        a = fa2_b200.backward(Q, K, V, O, G1, L)
+        b = fa2_b200.backward(Q, K, V, O, G2, L)
+        c = fa2_b200.backward(Q, K, V, O, (G1 + G2).contiguous(), L)
+        for x, y, z in zip(a, b, c):
+            assert float((z - (x + y)).abs().max()) < 2e-2
+        q, k, v, go = (t[0, 0].double() for t in (Q, K, V, G1))
+        s = (q @ k.T) / (D ** 0.5)
+        P = torch.softmax(s, -1)
+        o = P @ v
+        dV = P.T @ go
+        dP = go @ v.T
+        dS = P * (dP - (go * o).sum(-1, keepdim=True)) / (D ** 0.5)
+        assert float((a[2][0, 0].double() - dV).abs().max()) < 1e-2
+        assert float((a[0][0, 0].double() - dS @ k).abs().max()) < 1e-2
+        assert float((a[1][0, 0].double() - dS.T @ q).abs().max()) < 1e-2
+
+
+def test_host_api_backward_default_dO_is_ones(U):
+    """CLI rule: no dO.bin -> dO = 1 (src/main.cpp:83-93)."""
+    import fa2_b200
+    Q, K, V, _ = U.randn_case((1, 2, 160, 64), seed=8)
+    (O, L, dQ, dK, dV), secs = fa2_b200.run_flash_attention(Q, K, V, mode="forward_backward")
+    t = U.orc.attention_fp64(Q, K, V, np.ones_like(Q))
+    for got, want in zip((O, L, dQ, dK, dV), t):
+        assert U.maxerr(got, want) < 1e-2
+    (dQ2, dK2, dV2), _ = fa2_b200.run_flash_attention(Q, K, V, O, L, mode="backward")
+    assert U.maxerr(dK2, dK) < 1e-5 and U.maxerr(dV2, dV) < 1e-5 and U.maxerr(dQ2, dQ) < 1e-4
