@@ -23,7 +23,7 @@ namespace {
 constexpr int BM = 128;         // query rows per tile
 constexpr int BN = 128;         // kv rows per tile
 constexpr int KV_STAGES = 2;
-constexpr int NUM_THREADS = 320;
+constexpr int NUM_THREADS = 384;        // 3 warpgroups; warps 10, 11 only donate registers
 constexpr int MMA_WARP = 8;
 constexpr int TMA_WARP = 9;
 constexpr float RESCALE_THRESHOLD = 8.0f;   // log2 units
@@ -36,13 +36,13 @@ struct FwdSmem {
     static constexpr int OFF_K = OFF_Q + 2 * TILE_BYTES;      // KV_STAGES tiles
     static constexpr int OFF_V = OFF_K + KV_STAGES * TILE_BYTES;
     static constexpr int OFF_BAR = OFF_V + KV_STAGES * TILE_BYTES;
-    static constexpr int NUM_BARS = 2 + 4 * KV_STAGES + 2 + 2 + 2;
+    static constexpr int NUM_BARS = 2 + 4 * KV_STAGES + 2 + 4 + 2;
     static constexpr int OFF_TMEM_PTR = OFF_BAR + NUM_BARS * 8;
     static constexpr int BYTES = OFF_TMEM_PTR + 16;
     static constexpr int ALLOC = BYTES + 1024;                // slack for manual 1024-B alignment
 };
 
-template <int DP>
+template <int DP, bool BF16>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 fa2_fwd_kernel(const __grid_constant__ FwdParams p) {
     using L = FwdSmem<DP>;
@@ -60,8 +60,8 @@ fa2_fwd_kernel(const __grid_constant__ FwdParams p) {
     uint64_t* v_full = k_empty + KV_STAGES;
     uint64_t* v_empty = v_full + KV_STAGES;
     uint64_t* s_full = v_empty + KV_STAGES;        // [2]
-    uint64_t* p_full = s_full + 2;                 // [2]
-    uint64_t* o_full = p_full + 2;                 // [2]
+    uint64_t* p_full = s_full + 2;                 // [2 tiles][2 halves of the KV columns]
+    uint64_t* o_full = p_full + 4;                 // [2]
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + L::OFF_TMEM_PTR);
 
     const int warp = threadIdx.x >> 5;
@@ -83,7 +83,8 @@ fa2_fwd_kernel(const __grid_constant__ FwdParams p) {
             for (int i = 0; i < 2; ++i) {
                 mbar_init(&q_full[i], 1);
                 mbar_init(&s_full[i], 1);
-                mbar_init(&p_full[i], 4);       // one arrive per softmax warp
+                mbar_init(&p_full[2 * i], 4);       // one arrive per softmax warp
+                mbar_init(&p_full[2 * i + 1], 4);
                 mbar_init(&o_full[i], 1);
             }
             for (int i = 0; i < KV_STAGES; ++i) {
@@ -104,6 +105,7 @@ fa2_fwd_kernel(const __grid_constant__ FwdParams p) {
 
     if (warp == TMA_WARP) {
         // ------------------------------------------------------------------ TMA producer
+        setmaxnreg_dec<56>();
         if (lane == 0) {
             for (int t = 0; t < n_qt; ++t) {
                 mbar_expect_tx(&q_full[t], L::TILE_BYTES);
@@ -128,33 +130,34 @@ fa2_fwd_kernel(const __grid_constant__ FwdParams p) {
         }
     } else if (warp == MMA_WARP) {
         // ------------------------------------------------------------------ MMA issuer
+        setmaxnreg_dec<56>();
         if (lane == 0) {
-            const uint32_t idesc_qk = umma_idesc_f16(BM, BN, 0, 0, p.bf16);
-            const uint32_t idesc_pv = umma_idesc_f16(BM, DP, 0, 1, p.bf16);
-            const uint32_t q_addr = smem_u32(smem + L::OFF_Q);
-            const uint32_t k_addr = smem_u32(smem + L::OFF_K);
-            const uint32_t v_addr = smem_u32(smem + L::OFF_V);
-            const uint32_t col_s[2] = {COL_S0, COL_S1};
-            const uint32_t col_o[2] = {COL_O0, COL_O1};
+            const uint32_t idesc_qk = umma_idesc_f16(BM, BN, 0, 0, BF16 ? 1 : 0);
+            const uint32_t idesc_pv = umma_idesc_f16(BM, DP, 0, 1, BF16 ? 1 : 0);
+            const uint32_t hi = umma_desc_hi(1024);
+            const uint32_t q_lo = umma_desc_lo(smem_u32(smem + L::OFF_Q), 16);
+            const uint32_t k_lo = umma_desc_lo(smem_u32(smem + L::OFF_K), 16);
+            const uint32_t v_lo = umma_desc_lo(smem_u32(smem + L::OFF_V), L::ATOM_BYTES);   // LBO = next 64-col chunk
+            constexpr uint32_t TILE16 = L::TILE_BYTES >> 4;
 
             auto issue_qk = [&](int t, int s) {
                 // S_t = Q_t K^T : A, B both K-major, DP/64 swizzle atoms, 4 K-steps of 32 B per atom
-#pragma unroll
-                for (int k = 0; k < KSTEPS_QK; ++k) {
-                    const uint32_t off = (k >> 2) * L::ATOM_BYTES + (k & 3) * 32;
-                    umma_ss(tmem_base + col_s[t],
-                            umma_smem_desc(q_addr + t * L::TILE_BYTES + off, 16, 1024),
-                            umma_smem_desc(k_addr + s * L::TILE_BYTES + off, 16, 1024), idesc_qk, k > 0);
-                }
+                const uint32_t d = tmem_base + (t ? COL_S1 : COL_S0);
+                const uint32_t a = q_lo + t * TILE16, b = k_lo + s * TILE16;
+                static_for<KSTEPS_QK>([&](auto kk) {
+                    constexpr int k = decltype(kk)::value;
+                    umma_ss_off<koff_kmajor(k, L::ATOM_BYTES), koff_kmajor(k, L::ATOM_BYTES)>(d, a, b, hi, idesc_qk, k > 0);
+                });
             };
-            auto issue_pv = [&](int t, int s, bool first) {
-                // O_t += P_t V : A = P from TMEM (8 columns per K-step), B = V MN-major
-#pragma unroll
-                for (int k = 0; k < KSTEPS_PV; ++k) {
-                    umma_ts(tmem_base + col_o[t], tmem_base + col_s[t] + k * 8,
-                            umma_smem_desc(v_addr + s * L::TILE_BYTES + k * 2048, L::ATOM_BYTES, 1024), idesc_pv,
-                            (!first || k > 0) ? 1u : 0u);
-                }
+            auto issue_pv = [&](int t, int s, bool first, auto half) {
+                // O_t += P_t V : A = P from TMEM (8 columns per K-step), B = V MN-major; one half = 64 KV rows
+                constexpr int h = decltype(half)::value;
+                const uint32_t d = tmem_base + (t ? COL_O1 : COL_O0);
+                const uint32_t a = tmem_base + (t ? COL_S1 : COL_S0), b = v_lo + s * TILE16;
+                static_for<KSTEPS_PV / 2>([&](auto kk) {
+                    constexpr int k = h * (KSTEPS_PV / 2) + decltype(kk)::value;
+                    umma_ts_off<k * 8, koff_mnmajor(k)>(d, a, b, hi, idesc_pv, (!first || k > 0) ? 1u : 0u);
+                });
             };
 
             mbar_wait(&k_full[0], 0);
@@ -172,9 +175,12 @@ fa2_fwd_kernel(const __grid_constant__ FwdParams p) {
                 const uint32_t ph1 = ((j + 1) / KV_STAGES) & 1;
                 mbar_wait(&v_full[s], ph);
                 for (int t = 0; t < n_qt; ++t) {
-                    mbar_wait(&p_full[t], j & 1);
+                    mbar_wait(&p_full[2 * t], j & 1);
                     tc_fence_after();
-                    issue_pv(t, s, j == 0);
+                    issue_pv(t, s, j == 0, std::integral_constant<int, 0>{});
+                    mbar_wait(&p_full[2 * t + 1], j & 1);
+                    tc_fence_after();
+                    issue_pv(t, s, j == 0, std::integral_constant<int, 1>{});
                     if (t == n_qt - 1) umma_commit(&v_empty[s]);
                     if (j + 1 < n_kv) {
                         if (t == 0) {
@@ -190,8 +196,12 @@ fa2_fwd_kernel(const __grid_constant__ FwdParams p) {
                 }
             }
         }
-    } else if (warp < 4 * n_qt) {
+    } else if (warp >= 8) {
+        setmaxnreg_dec<56>();          // warps 10, 11: register donors only
+    } else {
         // ------------------------------------------------------------------ softmax + epilogue
+        setmaxnreg_inc<224>();
+        if (warp < 4 * n_qt) {
         const int t = warp >> 2;
         const int row_in_tile = (warp & 3) * 32 + lane;
         const int q_row = q_row0 + t * BM + row_in_tile;
@@ -252,26 +262,34 @@ fa2_fwd_kernel(const __grid_constant__ FwdParams p) {
                 }
             }
 
-            // P = 2^(S*c2 - m*c2), packed to 16 bit and written over S (all of S is already in registers)
+            // P = 2^(S*c2 - m*c2) with packed fp32x2 math, rounded to 16 bit and written over S (all of S is
+            // already in registers); handed to the MMA warp in two halves so P V can start early.
             const float neg_m = -m_ref * c2;
-            float lsum[4] = {0.f, 0.f, 0.f, 0.f};
+            const float2 c2v = make_float2(c2, c2), nmv = make_float2(neg_m, neg_m);
+            float2 ls0 = make_float2(0.f, 0.f), ls1 = make_float2(0.f, 0.f);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 uint32_t pk[16];
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    const float e0 = ex2_approx(fmaf(__uint_as_float(sr[c][i]), c2, neg_m));
-                    const float e1 = ex2_approx(fmaf(__uint_as_float(sr[c][i + 1]), c2, neg_m));
-                    lsum[c] += e0 + e1;
-                    pk[i >> 1] = p.bf16 ? pack_bf16x2(e0, e1) : pack_half2(e0, e1);
+                for (int i = 0; i < 32; i += 4) {
+                    const float2 x0 = __ffma2_rn(make_float2(__uint_as_float(sr[c][i]), __uint_as_float(sr[c][i + 1])), c2v, nmv);
+                    const float2 x1 = __ffma2_rn(make_float2(__uint_as_float(sr[c][i + 2]), __uint_as_float(sr[c][i + 3])), c2v, nmv);
+                    const float2 e0 = make_float2(ex2_approx(x0.x), ex2_approx(x0.y));
+                    const float2 e1 = make_float2(ex2_approx(x1.x), ex2_approx(x1.y));
+                    ls0 = __fadd2_rn(ls0, e0);
+                    ls1 = __fadd2_rn(ls1, e1);
+                    pk[i >> 1] = BF16 ? pack_bf16x2(e0.x, e0.y) : pack_half2(e0.x, e0.y);
+                    pk[(i >> 1) + 1] = BF16 ? pack_bf16x2(e1.x, e1.y) : pack_half2(e1.x, e1.y);
                 }
                 tmem_st16(t_s + c * 16, pk);
+                if (c & 1) {
+                    tmem_wait_st();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&p_full[2 * t + (c >> 1)]);
+                }
             }
-            l_run += (lsum[0] + lsum[1]) + (lsum[2] + lsum[3]);
-            tmem_wait_st();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&p_full[t]);
+            l_run += (ls0.x + ls0.y) + (ls1.x + ls1.y);
         }
 
         // epilogue: O / l -> fp32 global, LSE = ln(l) + m / sqrt(D)
@@ -299,6 +317,7 @@ fa2_fwd_kernel(const __grid_constant__ FwdParams p) {
         }
         if (row_ok)
             p.LSE[static_cast<size_t>(bh) * p.S + q_row] = m_ref * p.scale + logf(l_run);
+        }
     }
 
     tc_fence_before();
@@ -316,16 +335,15 @@ cudaError_t launch_fwd(const FwdParams& p, cudaStream_t st) {
     const int q_blocks = (p.S + 2 * BM - 1) / (2 * BM);
     const dim3 grid(static_cast<unsigned>(p.BH) * q_blocks);
     cudaError_t e;
-    if (DP == 64) {
-        e = cudaFuncSetAttribute(fa2_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem<64>::ALLOC);
-        if (e != cudaSuccess) return e;
-        fa2_fwd_kernel<64><<<grid, NUM_THREADS, FwdSmem<64>::ALLOC, st>>>(p);
-    } else {
-        e = cudaFuncSetAttribute(fa2_fwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 FwdSmem<128>::ALLOC);
-        if (e != cudaSuccess) return e;
-        fa2_fwd_kernel<128><<<grid, NUM_THREADS, FwdSmem<128>::ALLOC, st>>>(p);
-    }
+    auto go = [&](auto kern, int smem) -> cudaError_t {
+        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (err != cudaSuccess) return err;
+        kern<<<grid, NUM_THREADS, smem, st>>>(p);
+        return cudaSuccess;
+    };
+    if (DP == 64) e = p.bf16 ? go(fa2_fwd_kernel<64, true>, FwdSmem<64>::ALLOC) : go(fa2_fwd_kernel<64, false>, FwdSmem<64>::ALLOC);
+    else          e = p.bf16 ? go(fa2_fwd_kernel<128, true>, FwdSmem<128>::ALLOC) : go(fa2_fwd_kernel<128, false>, FwdSmem<128>::ALLOC);
+    if (e != cudaSuccess) return e;
     return cudaGetLastError();
 }
 

@@ -5,6 +5,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 
 namespace fa2 {
 
@@ -55,6 +56,16 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     uint32_t r;
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
     return r;
+}
+
+// register re-partitioning between warpgroups (every warp of the warpgroup must execute it)
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
 }
 
 // ----------------------------------------------------------------------------------------
@@ -213,6 +224,66 @@ __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64
         ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Register-lean forms for fully unrolled issue loops: the per-K-step offsets (in 16-byte units for smem
+// descriptors, in columns for TMEM) are immediates added inside the asm block, so the compiler keeps only
+// the base words live instead of hoisting one 64-bit descriptor per K-step.
+__host__ __device__ constexpr uint32_t umma_desc_hi(uint32_t sbo_bytes) {
+    return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (2u << 29);      // SBO | version 1 | SWIZZLE_128B
+}
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+    return ((saddr & 0x3FFFF) >> 4) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
+}
+template <uint32_t A_OFF, uint32_t B_OFF>
+__device__ __forceinline__ void umma_ss_off(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi,
+                                            uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b32 al, bl;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "add.u32 al, %1, %6;\n\t"
+        "add.u32 bl, %2, %7;\n\t"
+        "mov.b64 da, {al, %3};\n\t"
+        "mov.b64 db, {bl, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t"
+        "}\n"
+        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate), "n"(A_OFF), "n"(B_OFF)
+        : "memory");
+}
+template <uint32_t A_COL_OFF, uint32_t B_OFF>
+__device__ __forceinline__ void umma_ts_off(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t hi,
+                                            uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b32 at, bl;\n\t"
+        ".reg .b64 db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "add.u32 at, %1, %6;\n\t"
+        "add.u32 bl, %2, %7;\n\t"
+        "mov.b64 db, {bl, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [at], db, %4, p;\n\t"
+        "}\n"
+        ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate), "n"(A_COL_OFF), "n"(B_OFF)
+        : "memory");
+}
+// K-step offsets (16-byte units): K-major operand = atom (k/4) of [128 rows][128 B] + 32 B per step;
+// MN-major operand = 16 rows of 128 B per step.
+__host__ __device__ constexpr uint32_t koff_kmajor(int k, int atom_bytes) {
+    return static_cast<uint32_t>(((k >> 2) * atom_bytes + (k & 3) * 32) >> 4);
+}
+__host__ __device__ constexpr uint32_t koff_mnmajor(int k) { return static_cast<uint32_t>((k * 2048) >> 4); }
+
+// compile-time loop: f(std::integral_constant<int, 0>{}), ..., f(integral_constant<int, N-1>{})
+template <int N, int I = 0, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for<N, I + 1>(f);
+    }
+}
+
 // Arrive on an mbarrier once every tcgen05 op issued so far by this thread has completed.
 // (implies tcgen05.fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
