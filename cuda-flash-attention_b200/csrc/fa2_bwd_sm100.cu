@@ -12,9 +12,10 @@
 //     dK  += dS^T Q         (A = dS^T smem K-major,  B = Q tile MN-major)  -> TMEM [0,DP)
 //     dQ   = dS K           (A = dS^T smem read MN-major, B = K tile MN-major) -> TMEM [256,256+DP)
 // dQ shares its TMEM columns with dP^T (dP is dead once dS has been formed).
-// Warp roles (14 warps):  0-3 / 4-7 compute (each warpgroup owns 64 of the 128 Q columns),
-// 8-11 dQ drain (TMEM -> swizzled smem -> cp.reduce.async.bulk.tensor add), 12 MMA issuer,
-// 13 TMA producer (also stages LSE and D_i per Q tile).
+// Warp roles (16 warps = 4 warpgroups):  0-3 / 4-7 compute (each warpgroup owns 64 of the 128 Q columns),
+// 8-11 dQ drain (TMEM -> registers -> swizzled smem -> cp.reduce.async.bulk.tensor add), 12 MMA issuer,
+// 13 TMA producer (also stages LSE and D_i per Q tile), 14-15 idle (they only donate registers:
+// setmaxnreg gives the compute warpgroups 160, the drain warpgroup 152 and the last warpgroup 40).
 // Padding needs no masks: TMA zero-fills out-of-range Q/K/V/dO rows, out-of-range LSE is
 // staged as +inf (P = 0), and out-of-range dK/dV rows are not stored.
 #include "fa2_common.h"
@@ -25,7 +26,7 @@ namespace {
 
 constexpr int BT = 128;                 // tile rows (both KV and Q)
 constexpr int ATOM = BT * 128;          // bytes of one [128 rows][64 x 16-bit] swizzle atom
-constexpr int NUM_THREADS = 448;
+constexpr int NUM_THREADS = 512;
 constexpr int DRAIN_WARP0 = 8;
 constexpr int MMA_WARP = 12;
 constexpr int TMA_WARP = 13;
@@ -48,7 +49,7 @@ struct BwdSmem {
     static constexpr int BYTES = OFF_TMEM_PTR + 16;
 };
 
-template <int DP>
+template <int DP, bool BF16>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
     using L = BwdSmem<DP>;
@@ -120,6 +121,7 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
 
     if (warp == TMA_WARP) {
         // ------------------------------------------------------------------ producer
+        setmaxnreg_dec<40>();
         if (lane == 0) {
             mbar_expect_tx(kv_full, 2 * L::TILE);
             for (int a = 0; a < DP / 64; ++a) {
@@ -158,48 +160,51 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
         }
     } else if (warp == MMA_WARP) {
         // ------------------------------------------------------------------ MMA issuer
+        setmaxnreg_dec<40>();
         if (lane == 0) {
-            const uint32_t id_ss = umma_idesc_f16(BT, BT, 0, 0, p.bf16);    // S^T, dP^T
-            const uint32_t id_kmn = umma_idesc_f16(BT, DP, 0, 1, p.bf16);   // dV, dK : A K-major, B MN-major
-            const uint32_t id_mnmn = umma_idesc_f16(BT, DP, 1, 1, p.bf16);  // dQ     : A MN-major, B MN-major
-            const uint32_t k_addr = smem_u32(smem + L::OFF_K);
-            const uint32_t v_addr = smem_u32(smem + L::OFF_V);
-            const uint32_t q_addr = smem_u32(smem + L::OFF_Q);
-            const uint32_t do_addr = smem_u32(smem + L::OFF_DO);
-            const uint32_t ds_addr = smem_u32(smem + L::OFF_DS);
+            const uint32_t id_ss = umma_idesc_f16(BT, BT, 0, 0, BF16 ? 1 : 0);    // S^T, dP^T
+            const uint32_t id_kmn = umma_idesc_f16(BT, DP, 0, 1, BF16 ? 1 : 0);   // dV, dK : A K-major, B MN-major
+            const uint32_t id_mnmn = umma_idesc_f16(BT, DP, 1, 1, BF16 ? 1 : 0);  // dQ     : A MN-major, B MN-major
+            const uint32_t hi = umma_desc_hi(1024);
+            // low descriptor words; "_k" = read K-major (LBO unused), "_mn" = read MN-major (LBO = next 64-wide chunk)
+            const uint32_t k_k = umma_desc_lo(smem_u32(smem + L::OFF_K), 16), k_mn = umma_desc_lo(smem_u32(smem + L::OFF_K), ATOM);
+            const uint32_t v_k = umma_desc_lo(smem_u32(smem + L::OFF_V), 16);
+            const uint32_t q_k = umma_desc_lo(smem_u32(smem + L::OFF_Q), 16), q_mn = umma_desc_lo(smem_u32(smem + L::OFF_Q), ATOM);
+            const uint32_t do_k = umma_desc_lo(smem_u32(smem + L::OFF_DO), 16), do_mn = umma_desc_lo(smem_u32(smem + L::OFF_DO), ATOM);
+            const uint32_t ds_k = umma_desc_lo(smem_u32(smem + L::OFF_DS), 16), ds_mn = umma_desc_lo(smem_u32(smem + L::OFF_DS), ATOM);
+            constexpr uint32_t TILE16 = L::TILE >> 4;
             const uint32_t tS = tmem_base + COL_S, tDP = tmem_base + COL_DP, tDQ = tmem_base + COL_DQ;
             const uint32_t tDK = tmem_base + COL_DK, tDV = tmem_base + COL_DV;
 
-            auto kmaj = [](uint32_t base, int k) {       // K-major operand, K-step k
-                return umma_smem_desc(base + (k >> 2) * ATOM + (k & 3) * 32, 16, 1024);
-            };
-            auto mnmaj = [](uint32_t base, int k) {      // MN-major operand, K-step k (16 rows of 128 B)
-                return umma_smem_desc(base + k * 2048, ATOM, 1024);
-            };
             auto issue_s = [&](int st) {
-#pragma unroll
-                for (int k = 0; k < KSTEPS_D; ++k)
-                    umma_ss(tS, kmaj(k_addr, k), kmaj(q_addr + st * L::TILE, k), id_ss, k > 0);
+                static_for<KSTEPS_D>([&](auto kk) {
+                    constexpr int k = decltype(kk)::value;
+                    umma_ss_off<koff_kmajor(k, ATOM), koff_kmajor(k, ATOM)>(tS, k_k, q_k + st * TILE16, hi, id_ss, k > 0);
+                });
             };
             auto issue_dp = [&]() {
-#pragma unroll
-                for (int k = 0; k < KSTEPS_D; ++k) umma_ss(tDP, kmaj(v_addr, k), kmaj(do_addr, k), id_ss, k > 0);
+                static_for<KSTEPS_D>([&](auto kk) {
+                    constexpr int k = decltype(kk)::value;
+                    umma_ss_off<koff_kmajor(k, ATOM), koff_kmajor(k, ATOM)>(tDP, v_k, do_k, hi, id_ss, k > 0);
+                });
             };
-            auto issue_dv = [&](bool first) {
-#pragma unroll
-                for (int k = 0; k < KSTEPS_T; ++k)     // P^T lives in two 32-column runs of the S region
-                    umma_ts(tDV, tS + (k >> 2) * 64 + (k & 3) * 8, mnmaj(do_addr, k), id_kmn,
-                            (!first || k > 0) ? 1u : 0u);
+            auto issue_dv = [&](bool first) {      // P^T lives in two 32-column runs of the S region
+                static_for<KSTEPS_T>([&](auto kk) {
+                    constexpr int k = decltype(kk)::value;
+                    umma_ts_off<(k >> 2) * 64 + (k & 3) * 8, koff_mnmajor(k)>(tDV, tS, do_mn, hi, id_kmn, (!first || k > 0) ? 1u : 0u);
+                });
             };
             auto issue_dk = [&](int st, bool first) {
-#pragma unroll
-                for (int k = 0; k < KSTEPS_T; ++k)
-                    umma_ss(tDK, kmaj(ds_addr, k), mnmaj(q_addr + st * L::TILE, k), id_kmn,
-                            (!first || k > 0) ? 1u : 0u);
+                static_for<KSTEPS_T>([&](auto kk) {
+                    constexpr int k = decltype(kk)::value;
+                    umma_ss_off<koff_kmajor(k, ATOM), koff_mnmajor(k)>(tDK, ds_k, q_mn + st * TILE16, hi, id_kmn, (!first || k > 0) ? 1u : 0u);
+                });
             };
             auto issue_dq = [&]() {
-#pragma unroll
-                for (int k = 0; k < KSTEPS_T; ++k) umma_ss(tDQ, mnmaj(ds_addr, k), mnmaj(k_addr, k), id_mnmn, k > 0);
+                static_for<KSTEPS_T>([&](auto kk) {
+                    constexpr int k = decltype(kk)::value;
+                    umma_ss_off<koff_mnmajor(k), koff_mnmajor(k)>(tDQ, ds_mn, k_mn, hi, id_mnmn, k > 0);
+                });
             };
 
             mbar_wait(kv_full, 0);
@@ -240,36 +245,43 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
         }
     } else if (warp < 8) {
         // ------------------------------------------------------------------ compute: P^T and dS^T
+        setmaxnreg_inc<160>();
         const int h = warp >> 2;                               // which 64 Q-columns of the tile
         const int n = (warp & 3) * 32 + lane;                  // kv row within the tile == TMEM lane
         const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
         const uint32_t tS = tmem_base + lane_addr + COL_S + h * 64;
         const uint32_t tDP = tmem_base + lane_addr + COL_DP + h * 64;
-        const float c2 = p.scale_log2;
+        const float2 c2v = make_float2(p.scale_log2, p.scale_log2);
         uint8_t* ds_atom = smem + L::OFF_DS + h * ATOM;        // Q columns [64h, 64h+64) = swizzle atom h
 
         for (int i = 0; i < n_tiles; ++i) {
             const int st = i % Q_STAGES;
-            const float* lse_t = lse_s + st * BT + h * 64;
-            const float* dl_t = delta_s + st * BT + h * 64;
+            const float4* lse_t = reinterpret_cast<const float4*>(lse_s + st * BT + h * 64);
+            const float4* dl_t = reinterpret_cast<const float4*>(delta_s + st * BT + h * 64);
             mbar_wait(&q_full[st], (i / Q_STAGES) & 1);        // LSE / D_i staging visible
             mbar_wait(s_full, i & 1);
             tc_fence_after();
-            uint32_t pk[32];                                    // P^T row, 64 values packed 2 x 16 bit
+            uint32_t sr[2][32];
+            tmem_ld32(tS, sr[0]);
+            tmem_ld32(tS + 32, sr[1]);
+            tmem_wait_ld();
+            float2 pf[32];                                      // P^T row (64 values) kept in fp32 for dS
+            uint32_t pk[32];                                    // the same, rounded to 16 bit for the dV MMA
 #pragma unroll
             for (int sub = 0; sub < 2; ++sub) {
-                uint32_t sr[32];
-                tmem_ld32(tS + sub * 32, sr);
-                tmem_wait_ld();
 #pragma unroll
                 for (int c = 0; c < 32; c += 4) {
-                    const float4 l4 = *reinterpret_cast<const float4*>(lse_t + sub * 32 + c);
-                    const float e0 = ex2_approx(fmaf(__uint_as_float(sr[c]), c2, -l4.x));
-                    const float e1 = ex2_approx(fmaf(__uint_as_float(sr[c + 1]), c2, -l4.y));
-                    const float e2 = ex2_approx(fmaf(__uint_as_float(sr[c + 2]), c2, -l4.z));
-                    const float e3 = ex2_approx(fmaf(__uint_as_float(sr[c + 3]), c2, -l4.w));
-                    pk[sub * 16 + (c >> 1)] = p.bf16 ? pack_bf16x2(e0, e1) : pack_half2(e0, e1);
-                    pk[sub * 16 + (c >> 1) + 1] = p.bf16 ? pack_bf16x2(e2, e3) : pack_half2(e2, e3);
+                    const float4 l4 = lse_t[(sub * 32 + c) >> 2];
+                    const float2 x0 = __ffma2_rn(make_float2(__uint_as_float(sr[sub][c]), __uint_as_float(sr[sub][c + 1])), c2v,
+                                                 make_float2(-l4.x, -l4.y));
+                    const float2 x1 = __ffma2_rn(make_float2(__uint_as_float(sr[sub][c + 2]), __uint_as_float(sr[sub][c + 3])), c2v,
+                                                 make_float2(-l4.z, -l4.w));
+                    const float2 e0 = make_float2(ex2_approx(x0.x), ex2_approx(x0.y));
+                    const float2 e1 = make_float2(ex2_approx(x1.x), ex2_approx(x1.y));
+                    pf[sub * 16 + (c >> 1)] = e0;
+                    pf[sub * 16 + (c >> 1) + 1] = e1;
+                    pk[sub * 16 + (c >> 1)] = BF16 ? pack_bf16x2(e0.x, e0.y) : pack_half2(e0.x, e0.y);
+                    pk[sub * 16 + (c >> 1) + 1] = BF16 ? pack_bf16x2(e1.x, e1.y) : pack_half2(e1.x, e1.y);
                 }
             }
             tmem_st32(tS, pk);                                  // over the S columns this thread already consumed
@@ -280,36 +292,35 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
 
             mbar_wait(dp_full, i & 1);
             tc_fence_after();
+            uint32_t dr[2][32];
+            tmem_ld32(tDP, dr[0]);
+            tmem_ld32(tDP + 32, dr[1]);
+            tmem_wait_ld();
+            tc_fence_before();              // dP reads are complete before dQ may overwrite the columns
             if (i > 0) mbar_wait(ds_empty, (i - 1) & 1);        // dK(i-1), dQ(i-1) finished reading dS smem
 #pragma unroll
             for (int sub = 0; sub < 2; ++sub) {
-                uint32_t dr[32];
-                tmem_ld32(tDP + sub * 32, dr);
-                tmem_wait_ld();
 #pragma unroll
                 for (int c8 = 0; c8 < 4; ++c8) {               // 8 columns -> one 16-byte chunk of dS^T
-                    uint32_t w[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int c = c8 * 8 + u * 2;
-                        const uint32_t pp = pk[sub * 16 + (c >> 1)];
-                        float p0, p1;
-                        if (p.bf16) {
-                            p0 = __uint_as_float(pp << 16);
-                            p1 = __uint_as_float(pp & 0xffff0000u);
-                        } else {
-                            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&pp));
-                            p0 = f.x; p1 = f.y;
-                        }
-                        const float2 d2 = *reinterpret_cast<const float2*>(dl_t + sub * 32 + c);
-                        const float s0 = p0 * (__uint_as_float(dr[c]) - d2.x);
-                        const float s1 = p1 * (__uint_as_float(dr[c + 1]) - d2.y);
-                        w[u] = p.bf16 ? pack_bf16x2(s0, s1) : pack_half2(s0, s1);
-                    }
-                    *reinterpret_cast<uint4*>(ds_atom + swz128(n, sub * 4 + c8)) = make_uint4(w[0], w[1], w[2], w[3]);
+                    const float4 da = dl_t[(sub * 32 + c8 * 8) >> 2];
+                    const float4 db = dl_t[((sub * 32 + c8 * 8) >> 2) + 1];
+                    const int c = c8 * 8;
+                    const float2 t0 = __fadd2_rn(make_float2(__uint_as_float(dr[sub][c]), __uint_as_float(dr[sub][c + 1])), make_float2(-da.x, -da.y));
+                    const float2 t1 = __fadd2_rn(make_float2(__uint_as_float(dr[sub][c + 2]), __uint_as_float(dr[sub][c + 3])), make_float2(-da.z, -da.w));
+                    const float2 t2 = __fadd2_rn(make_float2(__uint_as_float(dr[sub][c + 4]), __uint_as_float(dr[sub][c + 5])), make_float2(-db.x, -db.y));
+                    const float2 t3 = __fadd2_rn(make_float2(__uint_as_float(dr[sub][c + 6]), __uint_as_float(dr[sub][c + 7])), make_float2(-db.z, -db.w));
+                    const float2 s0 = __fmul2_rn(pf[sub * 16 + c8 * 4], t0);
+                    const float2 s1 = __fmul2_rn(pf[sub * 16 + c8 * 4 + 1], t1);
+                    const float2 s2 = __fmul2_rn(pf[sub * 16 + c8 * 4 + 2], t2);
+                    const float2 s3 = __fmul2_rn(pf[sub * 16 + c8 * 4 + 3], t3);
+                    uint4 w;
+                    w.x = BF16 ? pack_bf16x2(s0.x, s0.y) : pack_half2(s0.x, s0.y);
+                    w.y = BF16 ? pack_bf16x2(s1.x, s1.y) : pack_half2(s1.x, s1.y);
+                    w.z = BF16 ? pack_bf16x2(s2.x, s2.y) : pack_half2(s2.x, s2.y);
+                    w.w = BF16 ? pack_bf16x2(s3.x, s3.y) : pack_half2(s3.x, s3.y);
+                    *reinterpret_cast<uint4*>(ds_atom + swz128(n, sub * 4 + c8)) = w;
                 }
             }
-            tc_fence_before();              // dP reads are complete before dQ may overwrite the columns
             fence_proxy_async_smem();       // dS smem writes -> visible to the tensor core (async proxy)
             __syncwarp();
             if (lane == 0) mbar_arrive(ds_full);
@@ -342,6 +353,7 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
         }
     } else if (warp < 12) {
         // ------------------------------------------------------------------ dQ drain
+        setmaxnreg_inc<152>();
         const int wq = warp - DRAIN_WARP0;
         const int m = wq * 32 + lane;                          // Q row within the tile == TMEM lane
         const uint32_t tDQ = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + COL_DQ;
@@ -352,16 +364,15 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
         for (int i = 0; i < n_tiles; ++i) {
             mbar_wait(dq_full, i & 1);
             tc_fence_after();
+            uint32_t r[NCHUNK][32];
+#pragma unroll
+            for (int c = 0; c < NCHUNK; ++c) tmem_ld32(tDQ + c * 32, r[c]);
+            tmem_wait_ld();
+            tc_fence_before();                                  // whole dQ tile is in registers: release dP/dQ columns
+            __syncwarp();
+            if (lane == 0) mbar_arrive(dq_empty);
 #pragma unroll
             for (int c = 0; c < NCHUNK; ++c) {
-                uint32_t r[32];
-                tmem_ld32(tDQ + c * 32, r);
-                tmem_wait_ld();
-                if (c == NCHUNK - 1) {                          // last TMEM read of this tile: release dP/dQ columns
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(dq_empty);
-                }
                 if (c < n_chunk) {
                     uint8_t* stage = smem + L::OFF_DQS + (g & 1) * (BT * 128);
                     if (g >= 2) {                               // buffer was handed to TMA two chunks ago
@@ -371,10 +382,10 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
 #pragma unroll
                     for (int q4 = 0; q4 < 8; ++q4) {
                         float4 v4;
-                        v4.x = __uint_as_float(r[q4 * 4]) * p.scale;
-                        v4.y = __uint_as_float(r[q4 * 4 + 1]) * p.scale;
-                        v4.z = __uint_as_float(r[q4 * 4 + 2]) * p.scale;
-                        v4.w = __uint_as_float(r[q4 * 4 + 3]) * p.scale;
+                        v4.x = __uint_as_float(r[c][q4 * 4]) * p.scale;
+                        v4.y = __uint_as_float(r[c][q4 * 4 + 1]) * p.scale;
+                        v4.z = __uint_as_float(r[c][q4 * 4 + 2]) * p.scale;
+                        v4.w = __uint_as_float(r[c][q4 * 4 + 3]) * p.scale;
                         *reinterpret_cast<float4*>(stage + swz128(m, q4)) = v4;
                     }
                     fence_proxy_async_smem();
@@ -388,6 +399,8 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
             }
         }
         if (issuer) tma_store_wait<0>();
+    } else {
+        setmaxnreg_dec<40>();              // warps 14, 15: register donors only
     }
 
     tc_fence_before();
@@ -405,17 +418,26 @@ cudaError_t launch_bwd(const BwdParams& p, cudaStream_t st) {
     const int n_tiles = (p.S + BT - 1) / BT;
     const dim3 grid(static_cast<unsigned>(p.BH) * n_tiles);
     cudaError_t e;
-    if (DP == 64) {
-        e = cudaFuncSetAttribute(fa2_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem<64>::BYTES);
-        if (e != cudaSuccess) return e;
-        fa2_bwd_kernel<64><<<grid, NUM_THREADS, BwdSmem<64>::BYTES, st>>>(p);
-    } else {
-        e = cudaFuncSetAttribute(fa2_bwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 BwdSmem<128>::BYTES);
-        if (e != cudaSuccess) return e;
-        fa2_bwd_kernel<128><<<grid, NUM_THREADS, BwdSmem<128>::BYTES, st>>>(p);
-    }
+    auto go = [&](auto kern, int smem) -> cudaError_t {
+        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (err != cudaSuccess) return err;
+        kern<<<grid, NUM_THREADS, smem, st>>>(p);
+        return cudaSuccess;
+    };
+    if (DP == 64) e = p.bf16 ? go(fa2_bwd_kernel<64, true>, BwdSmem<64>::BYTES) : go(fa2_bwd_kernel<64, false>, BwdSmem<64>::BYTES);
+    else          e = p.bf16 ? go(fa2_bwd_kernel<128, true>, BwdSmem<128>::BYTES) : go(fa2_bwd_kernel<128, false>, BwdSmem<128>::BYTES);
+    if (e != cudaSuccess) return e;
     return cudaGetLastError();
+}
+
+
+cudaError_t warm_bwd() {
+    cudaFuncAttributes a;
+    cudaError_t e;
+    if ((e = cudaFuncGetAttributes(&a, fa2_bwd_kernel<64, false>)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&a, fa2_bwd_kernel<128, false>)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&a, fa2_bwd_kernel<64, true>)) != cudaSuccess) return e;
+    return cudaFuncGetAttributes(&a, fa2_bwd_kernel<128, true>);
 }
 
 }  // namespace fa2

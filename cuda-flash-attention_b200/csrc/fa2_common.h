@@ -50,5 +50,7 @@ cudaError_t launch_bwd_prepass(const float* O, const float* dO, const float* LSE
                                cudaStream_t st);
 cudaError_t launch_fwd(const FwdParams& p, cudaStream_t st);
 cudaError_t launch_bwd(const BwdParams& p, cudaStream_t st);
+cudaError_t warm_fwd();
+cudaError_t warm_bwd();
 
 }  // namespace fa2

@@ -347,4 +347,16 @@ cudaError_t launch_fwd(const FwdParams& p, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+
+// Forces the module/kernels to be loaded on the current device (lazy loading would otherwise land inside
+// the first timed launch).
+cudaError_t warm_fwd() {
+    cudaFuncAttributes a;
+    cudaError_t e;
+    if ((e = cudaFuncGetAttributes(&a, fa2_fwd_kernel<64, false>)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&a, fa2_fwd_kernel<128, false>)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&a, fa2_fwd_kernel<64, true>)) != cudaSuccess) return e;
+    return cudaFuncGetAttributes(&a, fa2_fwd_kernel<128, true>);
+}
+
 }  // namespace fa2
