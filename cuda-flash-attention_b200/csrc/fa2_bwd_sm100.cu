@@ -122,7 +122,7 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
     if (warp == TMA_WARP) {
         // ------------------------------------------------------------------ producer
         setmaxnreg_dec<40>();
-        if (lane == 0) {
+        if (elect_one()) {
             mbar_expect_tx(kv_full, 2 * L::TILE);
             for (int a = 0; a < DP / 64; ++a) {
                 tma_load_3d(smem + L::OFF_K + a * ATOM, &p.tm_k, kv_full, a * 64, kv_row0, bh);
@@ -133,7 +133,7 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
             const int s = i % Q_STAGES;
             const uint32_t ph = (i / Q_STAGES) & 1;
             mbar_wait(&q_empty[s], ph ^ 1);
-            if (lane == 0) {
+            if (elect_one()) {
                 mbar_expect_tx(&q_full[s], L::TILE);
                 for (int a = 0; a < DP / 64; ++a)
                     tma_load_3d(smem + L::OFF_Q + s * L::TILE + a * ATOM, &p.tm_q, &q_full[s], a * 64, i * BT, bh);
@@ -149,9 +149,9 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
                 delta_s[s * BT + m] = ok ? __ldg(p.delta + g) : 0.0f;
             }
             __syncwarp();
-            if (lane == 0) {
+            mbar_wait(do_empty, (i & 1) ^ 1);
+            if (elect_one()) {
                 mbar_arrive(&q_full[s]);
-                mbar_wait(do_empty, (i & 1) ^ 1);
                 mbar_expect_tx(do_full, L::TILE);
                 for (int a = 0; a < DP / 64; ++a)
                     tma_load_3d(smem + L::OFF_DO + a * ATOM, &p.tm_do, do_full, a * 64, i * BT, bh);
@@ -160,8 +160,10 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
         }
     } else if (warp == MMA_WARP) {
         // ------------------------------------------------------------------ MMA issuer
+        // The whole warp runs the loop (converged code lets the compiler keep descriptors in uniform
+        // registers); one elected lane issues each group of MMAs and its commits.
         setmaxnreg_dec<40>();
-        if (lane == 0) {
+        {
             const uint32_t id_ss = umma_idesc_f16(BT, BT, 0, 0, BF16 ? 1 : 0);    // S^T, dP^T
             const uint32_t id_kmn = umma_idesc_f16(BT, DP, 0, 1, BF16 ? 1 : 0);   // dV, dK : A K-major, B MN-major
             const uint32_t id_mnmn = umma_idesc_f16(BT, DP, 1, 1, BF16 ? 1 : 0);  // dQ     : A MN-major, B MN-major
@@ -212,35 +214,50 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
                 const int st = i % Q_STAGES;
                 mbar_wait(&q_full[st], (i / Q_STAGES) & 1);
                 tc_fence_after();
-                issue_s(st);                                   // S region is free: dV(i-1) was issued before
-                umma_commit(s_full);
+                if (elect_one()) {
+                    issue_s(st);                               // S region is free: dV(i-1) was issued before
+                    umma_commit(s_full);
+                }
+                __syncwarp();
                 if (i > 0) {
                     mbar_wait(ds_full, (i - 1) & 1);
                     tc_fence_after();
-                    issue_dq();                                // dQ(i-1) over the dead dP(i-1)
-                    umma_commit(dq_full);
-                    issue_dk((i - 1) % Q_STAGES, i == 1);      // dK += dS(i-1)^T Q(i-1)
-                    umma_commit(&q_empty[(i - 1) % Q_STAGES]);
-                    umma_commit(ds_empty);
+                    if (elect_one()) {
+                        issue_dq();                            // dQ(i-1) over the dead dP(i-1)
+                        umma_commit(dq_full);
+                        issue_dk((i - 1) % Q_STAGES, i == 1);  // dK += dS(i-1)^T Q(i-1)
+                        umma_commit(&q_empty[(i - 1) % Q_STAGES]);
+                        umma_commit(ds_empty);
+                    }
+                    __syncwarp();
                     mbar_wait(dq_empty, (i - 1) & 1);          // dQ(i-1) drained out of TMEM
                 }
                 mbar_wait(do_full, i & 1);
                 tc_fence_after();
-                issue_dp();
-                umma_commit(dp_full);
+                if (elect_one()) {
+                    issue_dp();
+                    umma_commit(dp_full);
+                }
+                __syncwarp();
                 mbar_wait(p_full, i & 1);
                 tc_fence_after();
-                issue_dv(i == 0);
-                umma_commit(do_empty);
+                if (elect_one()) {
+                    issue_dv(i == 0);
+                    umma_commit(do_empty);
+                }
+                __syncwarp();
             }
             {
                 const int i = n_tiles - 1;
                 mbar_wait(ds_full, i & 1);
                 tc_fence_after();
-                issue_dk(i % Q_STAGES, i == 0);
-                issue_dq();
-                umma_commit(dq_full);
-                umma_commit(dkdv_full);
+                if (elect_one()) {
+                    issue_dk(i % Q_STAGES, i == 0);
+                    issue_dq();
+                    umma_commit(dq_full);
+                    umma_commit(dkdv_full);
+                }
+                __syncwarp();
             }
         }
     } else if (warp < 8) {
@@ -264,24 +281,22 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
             uint32_t sr[2][32];
             tmem_ld32(tS, sr[0]);
             tmem_ld32(tS + 32, sr[1]);
+            uint32_t pk[32];                                    // P^T row (64 values) rounded to 16 bit
             tmem_wait_ld();
-            float2 pf[32];                                      // P^T row (64 values) kept in fp32 for dS
-            uint32_t pk[32];                                    // the same, rounded to 16 bit for the dV MMA
 #pragma unroll
             for (int sub = 0; sub < 2; ++sub) {
+                float4 l4[8];
 #pragma unroll
-                for (int c = 0; c < 32; c += 4) {
-                    const float4 l4 = lse_t[(sub * 32 + c) >> 2];
-                    const float2 x0 = __ffma2_rn(make_float2(__uint_as_float(sr[sub][c]), __uint_as_float(sr[sub][c + 1])), c2v,
-                                                 make_float2(-l4.x, -l4.y));
-                    const float2 x1 = __ffma2_rn(make_float2(__uint_as_float(sr[sub][c + 2]), __uint_as_float(sr[sub][c + 3])), c2v,
-                                                 make_float2(-l4.z, -l4.w));
-                    const float2 e0 = make_float2(ex2_approx(x0.x), ex2_approx(x0.y));
-                    const float2 e1 = make_float2(ex2_approx(x1.x), ex2_approx(x1.y));
-                    pf[sub * 16 + (c >> 1)] = e0;
-                    pf[sub * 16 + (c >> 1) + 1] = e1;
-                    pk[sub * 16 + (c >> 1)] = BF16 ? pack_bf16x2(e0.x, e0.y) : pack_half2(e0.x, e0.y);
-                    pk[sub * 16 + (c >> 1) + 1] = BF16 ? pack_bf16x2(e1.x, e1.y) : pack_half2(e1.x, e1.y);
+                for (int c = 0; c < 8; ++c) l4[c] = lse_t[sub * 8 + c];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float2 x0 = __ffma2_rn(make_float2(__uint_as_float(sr[sub][4 * c]), __uint_as_float(sr[sub][4 * c + 1])), c2v,
+                                                 make_float2(-l4[c].x, -l4[c].y));
+                    const float2 x1 = __ffma2_rn(make_float2(__uint_as_float(sr[sub][4 * c + 2]), __uint_as_float(sr[sub][4 * c + 3])), c2v,
+                                                 make_float2(-l4[c].z, -l4[c].w));
+                    const float e0 = ex2_approx(x0.x), e1 = ex2_approx(x0.y), e2 = ex2_approx(x1.x), e3 = ex2_approx(x1.y);
+                    pk[sub * 16 + 2 * c] = BF16 ? pack_bf16x2(e0, e1) : pack_half2(e0, e1);
+                    pk[sub * 16 + 2 * c + 1] = BF16 ? pack_bf16x2(e2, e3) : pack_half2(e2, e3);
                 }
             }
             tmem_st32(tS, pk);                                  // over the S columns this thread already consumed
@@ -298,27 +313,27 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
             tmem_wait_ld();
             tc_fence_before();              // dP reads are complete before dQ may overwrite the columns
             if (i > 0) mbar_wait(ds_empty, (i - 1) & 1);        // dK(i-1), dQ(i-1) finished reading dS smem
+            // dS^T = P^T o (dP^T - D_i): the difference in fp32, the product in packed 16-bit (it is rounded
+            // to 16 bit for the tensor core anyway)
 #pragma unroll
             for (int sub = 0; sub < 2; ++sub) {
+                float4 d4[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) d4[c] = dl_t[sub * 8 + c];
 #pragma unroll
                 for (int c8 = 0; c8 < 4; ++c8) {               // 8 columns -> one 16-byte chunk of dS^T
-                    const float4 da = dl_t[(sub * 32 + c8 * 8) >> 2];
-                    const float4 db = dl_t[((sub * 32 + c8 * 8) >> 2) + 1];
-                    const int c = c8 * 8;
-                    const float2 t0 = __fadd2_rn(make_float2(__uint_as_float(dr[sub][c]), __uint_as_float(dr[sub][c + 1])), make_float2(-da.x, -da.y));
-                    const float2 t1 = __fadd2_rn(make_float2(__uint_as_float(dr[sub][c + 2]), __uint_as_float(dr[sub][c + 3])), make_float2(-da.z, -da.w));
-                    const float2 t2 = __fadd2_rn(make_float2(__uint_as_float(dr[sub][c + 4]), __uint_as_float(dr[sub][c + 5])), make_float2(-db.x, -db.y));
-                    const float2 t3 = __fadd2_rn(make_float2(__uint_as_float(dr[sub][c + 6]), __uint_as_float(dr[sub][c + 7])), make_float2(-db.z, -db.w));
-                    const float2 s0 = __fmul2_rn(pf[sub * 16 + c8 * 4], t0);
-                    const float2 s1 = __fmul2_rn(pf[sub * 16 + c8 * 4 + 1], t1);
-                    const float2 s2 = __fmul2_rn(pf[sub * 16 + c8 * 4 + 2], t2);
-                    const float2 s3 = __fmul2_rn(pf[sub * 16 + c8 * 4 + 3], t3);
-                    uint4 w;
-                    w.x = BF16 ? pack_bf16x2(s0.x, s0.y) : pack_half2(s0.x, s0.y);
-                    w.y = BF16 ? pack_bf16x2(s1.x, s1.y) : pack_half2(s1.x, s1.y);
-                    w.z = BF16 ? pack_bf16x2(s2.x, s2.y) : pack_half2(s2.x, s2.y);
-                    w.w = BF16 ? pack_bf16x2(s3.x, s3.y) : pack_half2(s3.x, s3.y);
-                    *reinterpret_cast<uint4*>(ds_atom + swz128(n, sub * 4 + c8)) = w;
+                    uint32_t w[4];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const float4 dd = d4[c8 * 2 + u];
+                        const int c = c8 * 8 + u * 4;
+                        const float2 t0 = __fadd2_rn(make_float2(__uint_as_float(dr[sub][c]), __uint_as_float(dr[sub][c + 1])), make_float2(-dd.x, -dd.y));
+                        const float2 t1 = __fadd2_rn(make_float2(__uint_as_float(dr[sub][c + 2]), __uint_as_float(dr[sub][c + 3])), make_float2(-dd.z, -dd.w));
+                        const uint32_t p0 = pk[sub * 16 + c8 * 4 + u * 2], p1 = pk[sub * 16 + c8 * 4 + u * 2 + 1];
+                        w[u * 2] = BF16 ? mul_bf16x2(p0, pack_bf16x2(t0.x, t0.y)) : mul_half2(p0, pack_half2(t0.x, t0.y));
+                        w[u * 2 + 1] = BF16 ? mul_bf16x2(p1, pack_bf16x2(t1.x, t1.y)) : mul_half2(p1, pack_half2(t1.x, t1.y));
+                    }
+                    *reinterpret_cast<uint4*>(ds_atom + swz128(n, sub * 4 + c8)) = make_uint4(w[0], w[1], w[2], w[3]);
                 }
             }
             fence_proxy_async_smem();       // dS smem writes -> visible to the tensor core (async proxy)

@@ -106,32 +106,40 @@ fa2_fwd_kernel(const __grid_constant__ FwdParams p) {
     if (warp == TMA_WARP) {
         // ------------------------------------------------------------------ TMA producer
         setmaxnreg_dec<56>();
-        if (lane == 0) {
+        if (elect_one()) {
             for (int t = 0; t < n_qt; ++t) {
                 mbar_expect_tx(&q_full[t], L::TILE_BYTES);
                 for (int a = 0; a < DP / 64; ++a)
                     tma_load_3d(smem + L::OFF_Q + t * L::TILE_BYTES + a * L::ATOM_BYTES, &p.tm_q, &q_full[t],
                                 a * 64, q_row0 + t * BM, bh);
             }
-            for (int j = 0; j < n_kv; ++j) {
-                const int s = j % KV_STAGES;
-                const uint32_t ph = (j / KV_STAGES) & 1;
-                mbar_wait(&k_empty[s], ph ^ 1);
+        }
+        __syncwarp();
+        for (int j = 0; j < n_kv; ++j) {
+            const int s = j % KV_STAGES;
+            const uint32_t ph = (j / KV_STAGES) & 1;
+            mbar_wait(&k_empty[s], ph ^ 1);
+            if (elect_one()) {
                 mbar_expect_tx(&k_full[s], L::TILE_BYTES);
                 for (int a = 0; a < DP / 64; ++a)
                     tma_load_3d(smem + L::OFF_K + s * L::TILE_BYTES + a * L::ATOM_BYTES, &p.tm_k, &k_full[s],
                                 a * 64, j * BN, bh);
-                mbar_wait(&v_empty[s], ph ^ 1);
+            }
+            __syncwarp();
+            mbar_wait(&v_empty[s], ph ^ 1);
+            if (elect_one()) {
                 mbar_expect_tx(&v_full[s], L::TILE_BYTES);
                 for (int a = 0; a < DP / 64; ++a)
                     tma_load_3d(smem + L::OFF_V + s * L::TILE_BYTES + a * L::ATOM_BYTES, &p.tm_v, &v_full[s],
                                 a * 64, j * BN, bh);
             }
+            __syncwarp();
         }
     } else if (warp == MMA_WARP) {
         // ------------------------------------------------------------------ MMA issuer
+        // whole warp runs the loop (converged); one elected lane issues each MMA group and its commits
         setmaxnreg_dec<56>();
-        if (lane == 0) {
+        {
             const uint32_t idesc_qk = umma_idesc_f16(BM, BN, 0, 0, BF16 ? 1 : 0);
             const uint32_t idesc_pv = umma_idesc_f16(BM, DP, 0, 1, BF16 ? 1 : 0);
             const uint32_t hi = umma_desc_hi(1024);
@@ -164,10 +172,13 @@ fa2_fwd_kernel(const __grid_constant__ FwdParams p) {
             for (int t = 0; t < n_qt; ++t) {
                 mbar_wait(&q_full[t], 0);
                 tc_fence_after();
-                issue_qk(t, 0);
-                umma_commit(&s_full[t]);
+                if (elect_one()) {
+                    issue_qk(t, 0);
+                    umma_commit(&s_full[t]);
+                    if (t == n_qt - 1) umma_commit(&k_empty[0]);   // K(0) is free once every S(0) has been computed
+                }
+                __syncwarp();
             }
-            umma_commit(&k_empty[0]);   // K(0) is free once every S(0) has been computed
             for (int j = 0; j < n_kv; ++j) {
                 const int s = j % KV_STAGES;
                 const uint32_t ph = (j / KV_STAGES) & 1;
@@ -177,22 +188,23 @@ fa2_fwd_kernel(const __grid_constant__ FwdParams p) {
                 for (int t = 0; t < n_qt; ++t) {
                     mbar_wait(&p_full[2 * t], j & 1);
                     tc_fence_after();
-                    issue_pv(t, s, j == 0, std::integral_constant<int, 0>{});
+                    if (elect_one()) issue_pv(t, s, j == 0, std::integral_constant<int, 0>{});
+                    __syncwarp();
                     mbar_wait(&p_full[2 * t + 1], j & 1);
+                    if (j + 1 < n_kv && t == 0) mbar_wait(&k_full[s1], ph1);
                     tc_fence_after();
-                    issue_pv(t, s, j == 0, std::integral_constant<int, 1>{});
-                    if (t == n_qt - 1) umma_commit(&v_empty[s]);
-                    if (j + 1 < n_kv) {
-                        if (t == 0) {
-                            mbar_wait(&k_full[s1], ph1);
-                            tc_fence_after();
+                    if (elect_one()) {
+                        issue_pv(t, s, j == 0, std::integral_constant<int, 1>{});
+                        if (t == n_qt - 1) umma_commit(&v_empty[s]);
+                        if (j + 1 < n_kv) {
+                            issue_qk(t, s1);
+                            umma_commit(&s_full[t]);
+                            if (t == n_qt - 1) umma_commit(&k_empty[s1]);
+                        } else {
+                            umma_commit(&o_full[t]);
                         }
-                        issue_qk(t, s1);
-                        umma_commit(&s_full[t]);
-                        if (t == n_qt - 1) umma_commit(&k_empty[s1]);
-                    } else {
-                        umma_commit(&o_full[t]);
                     }
+                    __syncwarp();
                 }
             }
         }

@@ -58,6 +58,17 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     return r;
 }
 
+__device__ __forceinline__ uint32_t mul_half2(uint32_t a, uint32_t b) {
+    uint32_t r;
+    asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+__device__ __forceinline__ uint32_t mul_bf16x2(uint32_t a, uint32_t b) {
+    uint32_t r;
+    asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+
 // register re-partitioning between warpgroups (every warp of the warpgroup must execute it)
 template <int N>
 __device__ __forceinline__ void setmaxnreg_inc() {
