@@ -181,6 +181,8 @@ int prepare(Prepared* pr, int B, int H, int S, int D, int precision, bool backwa
     return FA2_OK;
 }
 
+unsigned long long* g_timeline = nullptr;   // set by fa2_debug_set_timeline (debug builds)
+
 // optional per-kernel timing (fa2_profile_enable / fa2_profile_read)
 bool g_profile = false;
 struct ProfSpan { int kind; cudaEvent_t a, b; };
@@ -233,6 +235,7 @@ int run_bwd_main(const Prepared& pr, const float* O, const float* dO, const floa
     if ((rc = make_tmap_f32(&p.tm_dq, dQ, pr.BH, pr.S, pr.D))) return rc;
     p.lse_log2 = lse2; p.delta = delta; p.dQ = dQ; p.dK = dK; p.dV = dV;
     p.BH = pr.BH; p.S = pr.S; p.D = pr.D; p.scale = pr.scale; p.scale_log2 = pr.scale_log2; p.bf16 = pr.bf16;
+    p.timeline = g_timeline;
     ProfScope prof(3, st);
     FA2_CUDA(launch_bwd(p, st));
     return FA2_OK;
@@ -430,6 +433,13 @@ void fa2_host_free(void* p) {
     }
     free(p);
 }
+
+#ifdef FA2_TIMELINE
+int fa2_debug_set_timeline(void* dev_ptr) {
+    g_timeline = static_cast<unsigned long long*>(dev_ptr);
+    return FA2_OK;
+}
+#endif
 
 int fa2_profile_enable(int on) {
     g_profile = on != 0;

@@ -12,10 +12,17 @@
 //     dK  += dS^T Q         (A = dS^T smem K-major,  B = Q tile MN-major)  -> TMEM [0,DP)
 //     dQ   = dS K           (A = dS^T smem read MN-major, B = K tile MN-major) -> TMEM [256,256+DP)
 // dQ shares its TMEM columns with dP^T (dP is dead once dS has been formed).
-// Warp roles (16 warps = 4 warpgroups):  0-3 / 4-7 compute (each warpgroup owns 64 of the 128 Q columns),
-// 8-11 dQ drain (TMEM -> registers -> swizzled smem -> cp.reduce.async.bulk.tensor add), 12 MMA issuer,
-// 13 TMA producer (also stages LSE and D_i per Q tile), 14-15 idle (they only donate registers:
-// setmaxnreg gives the compute warpgroups 160, the drain warpgroup 152 and the last warpgroup 40).
+//
+// Warp roles (20 warps = 5 warpgroups; within a pair of warpgroups, warpgroup h owns one half of the columns):
+//   0-3 / 4-7    compute:  S^T -> P^T = 2^(S^T c - lse2[q]) -> 16-bit into TMEM for the dV MMA, then
+//                          dS^T = P^T o (dP^T - D_i[q]) -> 128B-swizzled smem; at the end they store dK / dV
+//   8-11 / 12-15 dQ drain: TMEM -> registers (frees the dP/dQ columns at once) -> scaled, swizzled smem ->
+//                          cp.reduce.async.bulk.tensor add.  fp32 reduce-add sustains only ~24 B/clk per SM
+//                          (tools/reduce_probe.cu), i.e. >= 2730 cycles per 64 KB dQ tile, so the drain must never
+//                          hold anything else up: each drain warpgroup has two 16 KB buffers -- a dedicated one and
+//                          "its" half of the dS tile, which is dead between dK(i)/dQ(i) and the write of dS(i+1).
+//   16 MMA issuer, 17 TMA producer (also stages LSE and D_i per Q tile), 18-19 register donors.
+// The CTA launches with 640 x 96 registers; setmaxnreg moves them to compute 128 / drain 88 / rest 40.
 // Padding needs no masks: TMA zero-fills out-of-range Q/K/V/dO rows, out-of-range LSE is
 // staged as +inf (P = 0), and out-of-range dK/dV rows are not stored.
 #include "fa2_common.h"
@@ -26,11 +33,18 @@ namespace {
 
 constexpr int BT = 128;                 // tile rows (both KV and Q)
 constexpr int ATOM = BT * 128;          // bytes of one [128 rows][64 x 16-bit] swizzle atom
-constexpr int NUM_THREADS = 512;
-constexpr int DRAIN_WARP0 = 8;
-constexpr int MMA_WARP = 12;
-constexpr int TMA_WARP = 13;
+constexpr int NUM_THREADS = 640;
+constexpr int D_WARP0 = 8;
+constexpr int MMA_WARP = 16;
+constexpr int TMA_WARP = 17;
 constexpr int Q_STAGES = 2;
+
+// Debug timeline (only with -DFA2_TIMELINE): lane 0 of a role stamps clock64 into slot `slot` of iteration i.
+#ifdef FA2_TIMELINE
+#define TL(slot) do { if (p.timeline && blockIdx.x == 0 && lane == 0 && i < 32) p.timeline[i * 32 + (slot)] = clock64(); } while (0)
+#else
+#define TL(slot) do { } while (0)
+#endif
 
 template <int DP>
 struct BwdSmem {
@@ -40,7 +54,7 @@ struct BwdSmem {
     static constexpr int OFF_Q = OFF_V + TILE;                    // Q_STAGES tiles
     static constexpr int OFF_DO = OFF_Q + Q_STAGES * TILE;        // 1 tile
     static constexpr int OFF_DS = OFF_DO + TILE;                  // [128 kv][128 q] 16-bit, 2 atoms
-    static constexpr int OFF_DQS = OFF_DS + 2 * ATOM;             // 2 x [128][32] fp32 staging
+    static constexpr int OFF_DQS = OFF_DS + 2 * ATOM;             // 2 x [128][32] fp32 staging (one per D warpgroup)
     static constexpr int OFF_LSE = OFF_DQS + 2 * BT * 128;        // Q_STAGES x 128 fp32
     static constexpr int OFF_DELTA = OFF_LSE + Q_STAGES * BT * 4;
     static constexpr int OFF_BAR = OFF_DELTA + Q_STAGES * BT * 4;
@@ -73,6 +87,7 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
     uint64_t* dq_full = bars + 12;
     uint64_t* dq_empty = bars + 13;
     uint64_t* dkdv_full = bars + 14;
+    uint64_t* atom_free = bars + 15;
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + L::OFF_TMEM_PTR);
     float* lse_s = reinterpret_cast<float*>(smem + L::OFF_LSE);
     float* delta_s = reinterpret_cast<float*>(smem + L::OFF_DELTA);
@@ -82,7 +97,11 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
 
     const int n_tiles = (p.S + BT - 1) / BT;       // same count for KV and Q tiles
     const int bh = blockIdx.x / n_tiles;
-    const int kv_row0 = (blockIdx.x % n_tiles) * BT;
+    const int kv_tile = blockIdx.x % n_tiles;
+    const int kv_row0 = kv_tile * BT;
+    // Every CTA of a (b,h) slab walks the Q tiles in a different rotation, so that at any moment the
+    // concurrently running CTAs reduce-add into DIFFERENT dQ tiles (no same-address contention in L2).
+    auto q_row_of = [&](int i) { int t = i + kv_tile; if (t >= n_tiles) t -= n_tiles; return t * BT; };
 
     if (warp == TMA_WARP && lane == 0) {
         tma_prefetch_desc(&p.tm_q);
@@ -103,11 +122,12 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
             mbar_init(do_empty, 1);
             mbar_init(s_full, 1);
             mbar_init(p_full, 8);             // one arrive per compute warp
+            mbar_init(atom_free, 2);          // one arrive per drain warpgroup: its half of the dS tile is reusable
             mbar_init(dp_full, 1);
-            mbar_init(ds_full, 8);
+            mbar_init(ds_full, 8);            // one arrive per compute warp
             mbar_init(ds_empty, 1);
             mbar_init(dq_full, 1);
-            mbar_init(dq_empty, 4);           // one arrive per drain warp
+            mbar_init(dq_empty, 8);           // one arrive per drain warp
             mbar_init(dkdv_full, 1);
             fence_mbar_init();
         }
@@ -136,13 +156,13 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
             if (elect_one()) {
                 mbar_expect_tx(&q_full[s], L::TILE);
                 for (int a = 0; a < DP / 64; ++a)
-                    tma_load_3d(smem + L::OFF_Q + s * L::TILE + a * ATOM, &p.tm_q, &q_full[s], a * 64, i * BT, bh);
+                    tma_load_3d(smem + L::OFF_Q + s * L::TILE + a * ATOM, &p.tm_q, &q_full[s], a * 64, q_row_of(i), bh);
             }
             // stage LSE (log2 domain) and D_i of this Q tile; rows past S: +inf / 0  => P = 0, dS = 0
 #pragma unroll
             for (int r = 0; r < BT / 32; ++r) {
                 const int m = r * 32 + lane;
-                const int row = i * BT + m;
+                const int row = q_row_of(i) + m;
                 const bool ok = row < p.S;
                 const size_t g = static_cast<size_t>(bh) * p.S + (ok ? row : 0);
                 lse_s[s * BT + m] = ok ? __ldg(p.lse_log2 + g) : INFINITY;
@@ -154,7 +174,7 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
                 mbar_arrive(&q_full[s]);
                 mbar_expect_tx(do_full, L::TILE);
                 for (int a = 0; a < DP / 64; ++a)
-                    tma_load_3d(smem + L::OFF_DO + a * ATOM, &p.tm_do, do_full, a * 64, i * BT, bh);
+                    tma_load_3d(smem + L::OFF_DO + a * ATOM, &p.tm_do, do_full, a * 64, q_row_of(i), bh);
             }
             __syncwarp();
         }
@@ -214,14 +234,16 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
                 const int st = i % Q_STAGES;
                 mbar_wait(&q_full[st], (i / Q_STAGES) & 1);
                 tc_fence_after();
+                TL(0);
                 if (elect_one()) {
-                    issue_s(st);                               // S region is free: dV(i-1) was issued before
+                    issue_s(st);                               // dV(i-1) was issued before, so P^T(i-1) is consumed
                     umma_commit(s_full);
                 }
                 __syncwarp();
                 if (i > 0) {
                     mbar_wait(ds_full, (i - 1) & 1);
                     tc_fence_after();
+                    TL(1);
                     if (elect_one()) {
                         issue_dq();                            // dQ(i-1) over the dead dP(i-1)
                         umma_commit(dq_full);
@@ -241,6 +263,7 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
                 __syncwarp();
                 mbar_wait(p_full, i & 1);
                 tc_fence_after();
+                TL(4);
                 if (elect_one()) {
                     issue_dv(i == 0);
                     umma_commit(do_empty);
@@ -255,14 +278,15 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
                     issue_dk(i % Q_STAGES, i == 0);
                     issue_dq();
                     umma_commit(dq_full);
+                    umma_commit(ds_empty);                     // the drain also waits for dS(n-1) to be dead
                     umma_commit(dkdv_full);
                 }
                 __syncwarp();
             }
         }
-    } else if (warp < 8) {
-        // ------------------------------------------------------------------ compute: P^T and dS^T
-        setmaxnreg_inc<160>();
+    } else if (warp < D_WARP0) {
+        // ------------------------------------------------------------------ compute warps: P^T and dS^T
+        setmaxnreg_inc<128>();
         const int h = warp >> 2;                               // which 64 Q-columns of the tile
         const int n = (warp & 3) * 32 + lane;                  // kv row within the tile == TMEM lane
         const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
@@ -278,25 +302,32 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
             mbar_wait(&q_full[st], (i / Q_STAGES) & 1);        // LSE / D_i staging visible
             mbar_wait(s_full, i & 1);
             tc_fence_after();
-            uint32_t sr[2][32];
-            tmem_ld32(tS, sr[0]);
-            tmem_ld32(tS + 32, sr[1]);
+            if (warp == 0) TL(8);
             uint32_t pk[32];                                    // P^T row (64 values) rounded to 16 bit
-            tmem_wait_ld();
+            {
+                uint32_t sr[2][32];
+                tmem_ld32(tS, sr[0]);
+                tmem_ld32(tS + 32, sr[1]);
+                tmem_wait_ld();
 #pragma unroll
-            for (int sub = 0; sub < 2; ++sub) {
-                float4 l4[8];
+                for (int sub = 0; sub < 2; ++sub) {
 #pragma unroll
-                for (int c = 0; c < 8; ++c) l4[c] = lse_t[sub * 8 + c];
+                    for (int hf = 0; hf < 2; ++hf) {
+                        float4 l4[4];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const float2 x0 = __ffma2_rn(make_float2(__uint_as_float(sr[sub][4 * c]), __uint_as_float(sr[sub][4 * c + 1])), c2v,
-                                                 make_float2(-l4[c].x, -l4[c].y));
-                    const float2 x1 = __ffma2_rn(make_float2(__uint_as_float(sr[sub][4 * c + 2]), __uint_as_float(sr[sub][4 * c + 3])), c2v,
-                                                 make_float2(-l4[c].z, -l4[c].w));
-                    const float e0 = ex2_approx(x0.x), e1 = ex2_approx(x0.y), e2 = ex2_approx(x1.x), e3 = ex2_approx(x1.y);
-                    pk[sub * 16 + 2 * c] = BF16 ? pack_bf16x2(e0, e1) : pack_half2(e0, e1);
-                    pk[sub * 16 + 2 * c + 1] = BF16 ? pack_bf16x2(e2, e3) : pack_half2(e2, e3);
+                        for (int c = 0; c < 4; ++c) l4[c] = lse_t[sub * 8 + hf * 4 + c];
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const int cc = hf * 4 + c;
+                            const float2 x0 = __ffma2_rn(make_float2(__uint_as_float(sr[sub][4 * cc]), __uint_as_float(sr[sub][4 * cc + 1])), c2v,
+                                                         make_float2(-l4[c].x, -l4[c].y));
+                            const float2 x1 = __ffma2_rn(make_float2(__uint_as_float(sr[sub][4 * cc + 2]), __uint_as_float(sr[sub][4 * cc + 3])), c2v,
+                                                         make_float2(-l4[c].z, -l4[c].w));
+                            const float e0 = ex2_approx(x0.x), e1 = ex2_approx(x0.y), e2 = ex2_approx(x1.x), e3 = ex2_approx(x1.y);
+                            pk[sub * 16 + 2 * cc] = BF16 ? pack_bf16x2(e0, e1) : pack_half2(e0, e1);
+                            pk[sub * 16 + 2 * cc + 1] = BF16 ? pack_bf16x2(e2, e3) : pack_half2(e2, e3);
+                        }
+                    }
                 }
             }
             tmem_st32(tS, pk);                                  // over the S columns this thread already consumed
@@ -304,41 +335,49 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(p_full);
+            if (warp == 0) TL(9);
 
             mbar_wait(dp_full, i & 1);
             tc_fence_after();
+            if (warp == 0) TL(10);
             uint32_t dr[2][32];
             tmem_ld32(tDP, dr[0]);
             tmem_ld32(tDP + 32, dr[1]);
             tmem_wait_ld();
             tc_fence_before();              // dP reads are complete before dQ may overwrite the columns
-            if (i > 0) mbar_wait(ds_empty, (i - 1) & 1);        // dK(i-1), dQ(i-1) finished reading dS smem
+            // the dS tile is reusable once dK(i-1)/dQ(i-1) have read it AND the drain has reduced out of it
+            if (i > 0) mbar_wait(atom_free, (i - 1) & 1);
             // dS^T = P^T o (dP^T - D_i): the difference in fp32, the product in packed 16-bit (it is rounded
             // to 16 bit for the tensor core anyway)
 #pragma unroll
             for (int sub = 0; sub < 2; ++sub) {
-                float4 d4[8];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) d4[c] = dl_t[sub * 8 + c];
+                for (int hf = 0; hf < 2; ++hf) {
+                    float4 d4[4];
 #pragma unroll
-                for (int c8 = 0; c8 < 4; ++c8) {               // 8 columns -> one 16-byte chunk of dS^T
-                    uint32_t w[4];
+                    for (int c = 0; c < 4; ++c) d4[c] = dl_t[sub * 8 + hf * 4 + c];
 #pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        const float4 dd = d4[c8 * 2 + u];
-                        const int c = c8 * 8 + u * 4;
-                        const float2 t0 = __fadd2_rn(make_float2(__uint_as_float(dr[sub][c]), __uint_as_float(dr[sub][c + 1])), make_float2(-dd.x, -dd.y));
-                        const float2 t1 = __fadd2_rn(make_float2(__uint_as_float(dr[sub][c + 2]), __uint_as_float(dr[sub][c + 3])), make_float2(-dd.z, -dd.w));
-                        const uint32_t p0 = pk[sub * 16 + c8 * 4 + u * 2], p1 = pk[sub * 16 + c8 * 4 + u * 2 + 1];
-                        w[u * 2] = BF16 ? mul_bf16x2(p0, pack_bf16x2(t0.x, t0.y)) : mul_half2(p0, pack_half2(t0.x, t0.y));
-                        w[u * 2 + 1] = BF16 ? mul_bf16x2(p1, pack_bf16x2(t1.x, t1.y)) : mul_half2(p1, pack_half2(t1.x, t1.y));
+                    for (int c8l = 0; c8l < 2; ++c8l) {        // 8 columns -> one 16-byte chunk of dS^T
+                        const int c8 = hf * 2 + c8l;
+                        uint32_t w[4];
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const float4 dd = d4[c8l * 2 + u];
+                            const int c = c8 * 8 + u * 4;
+                            const float2 t0 = __fadd2_rn(make_float2(__uint_as_float(dr[sub][c]), __uint_as_float(dr[sub][c + 1])), make_float2(-dd.x, -dd.y));
+                            const float2 t1 = __fadd2_rn(make_float2(__uint_as_float(dr[sub][c + 2]), __uint_as_float(dr[sub][c + 3])), make_float2(-dd.z, -dd.w));
+                            const uint32_t p0 = pk[sub * 16 + c8 * 4 + u * 2], p1 = pk[sub * 16 + c8 * 4 + u * 2 + 1];
+                            w[u * 2] = BF16 ? mul_bf16x2(p0, pack_bf16x2(t0.x, t0.y)) : mul_half2(p0, pack_half2(t0.x, t0.y));
+                            w[u * 2 + 1] = BF16 ? mul_bf16x2(p1, pack_bf16x2(t1.x, t1.y)) : mul_half2(p1, pack_half2(t1.x, t1.y));
+                        }
+                        *reinterpret_cast<uint4*>(ds_atom + swz128(n, sub * 4 + c8)) = make_uint4(w[0], w[1], w[2], w[3]);
                     }
-                    *reinterpret_cast<uint4*>(ds_atom + swz128(n, sub * 4 + c8)) = make_uint4(w[0], w[1], w[2], w[3]);
                 }
             }
             fence_proxy_async_smem();       // dS smem writes -> visible to the tensor core (async proxy)
             __syncwarp();
             if (lane == 0) mbar_arrive(ds_full);
+            if (warp == 0) TL(11);
         }
 
         // epilogue: warpgroup 0 stores dK (scaled by 1/sqrt(D)), warpgroup 1 stores dV
@@ -366,56 +405,70 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
                 }
             }
         }
-    } else if (warp < 12) {
-        // ------------------------------------------------------------------ dQ drain
-        setmaxnreg_inc<152>();
-        const int wq = warp - DRAIN_WARP0;
-        const int m = wq * 32 + lane;                          // Q row within the tile == TMEM lane
-        const uint32_t tDQ = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + COL_DQ;
-        const bool issuer = (warp == DRAIN_WARP0 && lane == 0);
-        constexpr int NCHUNK = DP / 32;
+    } else if (warp < MMA_WARP) {
+        // ------------------------------------------------------------------ dQ drain warps
+        setmaxnreg_dec<88>();
+        const int h = (warp - D_WARP0) >> 2;                   // head-dim half of dQ this warpgroup drains
+        const int n = (warp & 3) * 32 + lane;                  // TMEM lane == q row of the tile
+        const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
+        constexpr int CPW = DP / 64;                            // 32-column chunks per warpgroup (2 at D=128, else 1)
+        const uint32_t tDQ = tmem_base + lane_addr + COL_DQ + h * CPW * 32;
+        uint8_t* stage = smem + L::OFF_DQS + h * (BT * 128);   // dedicated 16 KB buffer
+        uint8_t* atom = smem + L::OFF_DS + h * ATOM;           // this warpgroup's half of the dS tile (16 KB)
+        const bool issuer = ((warp & 3) == 0) && lane == 0;
         const int n_chunk = (p.D + 31) / 32;                   // real columns only (D = 32 under DP = 64)
-        uint32_t g = 0;                                         // staging buffers handed to TMA so far
+        const uint32_t bar_id = 1 + 2 * h;                      // named barriers private to this warpgroup
+
+        auto put_chunk = [&](const uint32_t (&rc)[32], uint8_t* buf, int chunk, int i) {
+#pragma unroll
+            for (int q4 = 0; q4 < 8; ++q4) {
+                float4 v4;
+                v4.x = __uint_as_float(rc[q4 * 4]) * p.scale;
+                v4.y = __uint_as_float(rc[q4 * 4 + 1]) * p.scale;
+                v4.z = __uint_as_float(rc[q4 * 4 + 2]) * p.scale;
+                v4.w = __uint_as_float(rc[q4 * 4 + 3]) * p.scale;
+                *reinterpret_cast<float4*>(buf + swz128(n, q4)) = v4;
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(bar_id + 1, 128);
+            if (issuer) {
+                tma_reduce_add_3d(&p.tm_dq, buf, chunk * 32, q_row_of(i), bh);
+                tma_store_commit();
+            }
+        };
+
         for (int i = 0; i < n_tiles; ++i) {
             mbar_wait(dq_full, i & 1);
             tc_fence_after();
-            uint32_t r[NCHUNK][32];
+            if (warp == D_WARP0) TL(15);
+            uint32_t r[CPW][32];
 #pragma unroll
-            for (int c = 0; c < NCHUNK; ++c) tmem_ld32(tDQ + c * 32, r[c]);
+            for (int c = 0; c < CPW; ++c) tmem_ld32(tDQ + c * 32, r[c]);
             tmem_wait_ld();
-            tc_fence_before();                                  // whole dQ tile is in registers: release dP/dQ columns
+            tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(dq_empty);
-#pragma unroll
-            for (int c = 0; c < NCHUNK; ++c) {
-                if (c < n_chunk) {
-                    uint8_t* stage = smem + L::OFF_DQS + (g & 1) * (BT * 128);
-                    if (g >= 2) {                               // buffer was handed to TMA two chunks ago
-                        if (issuer) tma_store_wait_read<1>();
-                        named_bar_sync(1, 128);
-                    }
-#pragma unroll
-                    for (int q4 = 0; q4 < 8; ++q4) {
-                        float4 v4;
-                        v4.x = __uint_as_float(r[c][q4 * 4]) * p.scale;
-                        v4.y = __uint_as_float(r[c][q4 * 4 + 1]) * p.scale;
-                        v4.z = __uint_as_float(r[c][q4 * 4 + 2]) * p.scale;
-                        v4.w = __uint_as_float(r[c][q4 * 4 + 3]) * p.scale;
-                        *reinterpret_cast<float4*>(stage + swz128(m, q4)) = v4;
-                    }
-                    fence_proxy_async_smem();
-                    named_bar_sync(2, 128);
-                    if (issuer) {
-                        tma_reduce_add_3d(&p.tm_dq, stage, c * 32, i * BT, bh);
-                        tma_store_commit();
-                    }
-                    ++g;
-                }
+            if (lane == 0) mbar_arrive(dq_empty);               // dP(i+1) may overwrite the columns now
+            if (warp == D_WARP0) TL(16);
+
+            mbar_wait(ds_empty, i & 1);                         // dK(i), dQ(i) have finished reading dS(i)
+            if constexpr (CPW == 2) {
+                // first chunk through the (now dead) dS half: nothing of ours is pending on it
+                if (h * CPW < n_chunk) put_chunk(r[0], atom, h * CPW, i);
             }
+            // last chunk through the dedicated buffer: its previous reduce must have been read
+            if (issuer) tma_store_wait_read<(CPW == 2) ? 1 : 0>();
+            named_bar_sync(bar_id, 128);
+            if (h * CPW + CPW - 1 < n_chunk) put_chunk(r[CPW - 1], stage, h * CPW + CPW - 1, i);
+            // hand the dS half back to the compute warps once the reduce out of it has been read
+            if (issuer) {
+                if constexpr (CPW == 2) tma_store_wait_read<1>();
+                mbar_arrive(atom_free);
+            }
+            if (warp == D_WARP0) TL(17);
         }
         if (issuer) tma_store_wait<0>();
     } else {
-        setmaxnreg_dec<40>();              // warps 14, 15: register donors only
+        setmaxnreg_dec<40>();              // warps 18, 19: register donors only
     }
 
     tc_fence_before();

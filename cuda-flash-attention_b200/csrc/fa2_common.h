@@ -40,6 +40,7 @@ struct BwdParams {
     float scale_log2;
     float scale;
     int bf16;
+    unsigned long long* timeline;   // debug builds (-DFA2_TIMELINE) only: per-role clock64 stamps of CTA 0
 };
 
 // launchers (each returns a cudaError_t from the launch)

@@ -1,0 +1,35 @@
+#!/usr/bin/env python
+"""Debug: run the -DFA2_TIMELINE build of the backward kernel and print CTA 0's per-role timeline
+(clock64 stamps relative to the start of each iteration).  `make -C cuda-flash-attention_b200 timeline` first."""
+import ctypes
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+lib = ctypes.CDLL(os.path.join(ROOT, "cuda-flash-attention_b200", "build", "libfa2_b200_tl.so"))
+B, H, S, D = (int(x) for x in (sys.argv[1:5] if len(sys.argv) >= 5 else (1, 8, 4096, 128)))
+q, k, v, g = (torch.randn(B, H, S, D, device="cuda") for _ in range(4))
+o = torch.empty_like(q); l = torch.empty(B, H, S, device="cuda")
+dq, dk, dv = (torch.empty_like(q) for _ in range(3))
+tl = torch.zeros(32 * 32, dtype=torch.int64, device="cuda")
+vp = ctypes.c_void_p
+P = lambda t: vp(t.data_ptr())
+lib.fa2_forward(P(q), P(k), P(v), P(o), P(l), B, H, S, D, 1, None)
+for _ in range(2):
+    lib.fa2_backward(P(q), P(k), P(v), P(o), P(g), P(l), P(dq), P(dk), P(dv), B, H, S, D, 1, None)
+lib.fa2_debug_set_timeline(P(tl))
+lib.fa2_backward(P(q), P(k), P(v), P(o), P(g), P(l), P(dq), P(dk), P(dv), B, H, S, D, 1, None)
+torch.cuda.synchronize()
+t = tl.cpu().view(32, 32)
+names = {0: "MMA issue S", 1: "MMA ds_full(i-1) seen", 2: "MMA dq_empty(i-1) seen", 3: "MMA issue dP", 4: "MMA p_full seen/issue dV",
+         8: "C  s_full seen", 9: "C  p_full arrive", 10: "C  dp_full seen", 11: "C  ds_full arrive",
+         15: "Dr dq_full seen", 16: "Dr dq_empty arrive", 17: "Dr staging done"}
+base = int(t[8, 0])
+n_it = min(32, (S + 127) // 128)
+for i in range(8, min(n_it, 13)):
+    print(f"--- iteration {i} (period vs previous: {int(t[i,0]-t[i-1,0])} cycles)")
+    ev = sorted((int(t[i, s]), names[s]) for s in names if int(t[i, s]) > 0)
+    for c, nme in ev:
+        print(f"   {c - int(t[i,0]):7d}  {nme}")
