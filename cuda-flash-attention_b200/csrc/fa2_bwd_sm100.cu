@@ -18,9 +18,8 @@
 //                          dS^T = P^T o (dP^T - D_i[q]) -> 128B-swizzled smem; at the end they store dK / dV
 //   8-11 / 12-15 dQ drain: TMEM -> registers (frees the dP/dQ columns at once) -> scaled, swizzled smem ->
 //                          cp.reduce.async.bulk.tensor add.  fp32 reduce-add sustains only ~24 B/clk per SM
-//                          (tools/reduce_probe.cu), i.e. >= 2730 cycles per 64 KB dQ tile, so the drain must never
-//                          hold anything else up: each drain warpgroup has two 16 KB buffers -- a dedicated one and
-//                          "its" half of the dS tile, which is dead between dK(i)/dQ(i) and the write of dS(i+1).
+//                          (tools/reduce_probe.cu), i.e. >= 2730 cycles per 64 KB dQ tile -- more than the 2560
+//                          tensor cycles of the five GEMMs -- so only the drain warps ever wait for it.
 //   16 MMA issuer, 17 TMA producer (also stages LSE and D_i per Q tile), 18-19 register donors.
 // The CTA launches with 640 x 96 registers; setmaxnreg moves them to compute 128 / drain 88 / rest 40.
 // Padding needs no masks: TMA zero-fills out-of-range Q/K/V/dO rows, out-of-range LSE is
@@ -87,7 +86,6 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
     uint64_t* dq_full = bars + 12;
     uint64_t* dq_empty = bars + 13;
     uint64_t* dkdv_full = bars + 14;
-    uint64_t* atom_free = bars + 15;
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + L::OFF_TMEM_PTR);
     float* lse_s = reinterpret_cast<float*>(smem + L::OFF_LSE);
     float* delta_s = reinterpret_cast<float*>(smem + L::OFF_DELTA);
@@ -122,7 +120,6 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
             mbar_init(do_empty, 1);
             mbar_init(s_full, 1);
             mbar_init(p_full, 8);             // one arrive per compute warp
-            mbar_init(atom_free, 2);          // one arrive per drain warpgroup: its half of the dS tile is reusable
             mbar_init(dp_full, 1);
             mbar_init(ds_full, 8);            // one arrive per compute warp
             mbar_init(ds_empty, 1);
@@ -169,9 +166,10 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
                 delta_s[s * BT + m] = ok ? __ldg(p.delta + g) : 0.0f;
             }
             __syncwarp();
+            if (elect_one()) mbar_arrive(&q_full[s]);           // LSE / D_i staged (the Q tile itself lands via TMA)
+            __syncwarp();
             mbar_wait(do_empty, (i & 1) ^ 1);
             if (elect_one()) {
-                mbar_arrive(&q_full[s]);
                 mbar_expect_tx(do_full, L::TILE);
                 for (int a = 0; a < DP / 64; ++a)
                     tma_load_3d(smem + L::OFF_DO + a * ATOM, &p.tm_do, do_full, a * 64, q_row_of(i), bh);
@@ -278,7 +276,6 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
                     issue_dk(i % Q_STAGES, i == 0);
                     issue_dq();
                     umma_commit(dq_full);
-                    umma_commit(ds_empty);                     // the drain also waits for dS(n-1) to be dead
                     umma_commit(dkdv_full);
                 }
                 __syncwarp();
@@ -345,8 +342,7 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
             tmem_ld32(tDP + 32, dr[1]);
             tmem_wait_ld();
             tc_fence_before();              // dP reads are complete before dQ may overwrite the columns
-            // the dS tile is reusable once dK(i-1)/dQ(i-1) have read it AND the drain has reduced out of it
-            if (i > 0) mbar_wait(atom_free, (i - 1) & 1);
+            if (i > 0) mbar_wait(ds_empty, (i - 1) & 1);        // dK(i-1), dQ(i-1) finished reading dS smem
             // dS^T = P^T o (dP^T - D_i): the difference in fp32, the product in packed 16-bit (it is rounded
             // to 16 bit for the tensor core anyway)
 #pragma unroll
@@ -414,12 +410,13 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
         constexpr int CPW = DP / 64;                            // 32-column chunks per warpgroup (2 at D=128, else 1)
         const uint32_t tDQ = tmem_base + lane_addr + COL_DQ + h * CPW * 32;
         uint8_t* stage = smem + L::OFF_DQS + h * (BT * 128);   // dedicated 16 KB buffer
-        uint8_t* atom = smem + L::OFF_DS + h * ATOM;           // this warpgroup's half of the dS tile (16 KB)
         const bool issuer = ((warp & 3) == 0) && lane == 0;
         const int n_chunk = (p.D + 31) / 32;                   // real columns only (D = 32 under DP = 64)
         const uint32_t bar_id = 1 + 2 * h;                      // named barriers private to this warpgroup
 
-        auto put_chunk = [&](const uint32_t (&rc)[32], uint8_t* buf, int chunk, int i) {
+        auto put_chunk = [&](const uint32_t (&rc)[32], int chunk, int i) {
+            if (issuer) tma_store_wait_read<0>();               // previous reduce out of the buffer has been read
+            named_bar_sync(bar_id, 128);
 #pragma unroll
             for (int q4 = 0; q4 < 8; ++q4) {
                 float4 v4;
@@ -427,12 +424,12 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
                 v4.y = __uint_as_float(rc[q4 * 4 + 1]) * p.scale;
                 v4.z = __uint_as_float(rc[q4 * 4 + 2]) * p.scale;
                 v4.w = __uint_as_float(rc[q4 * 4 + 3]) * p.scale;
-                *reinterpret_cast<float4*>(buf + swz128(n, q4)) = v4;
+                *reinterpret_cast<float4*>(stage + swz128(n, q4)) = v4;
             }
             fence_proxy_async_smem();
             named_bar_sync(bar_id + 1, 128);
             if (issuer) {
-                tma_reduce_add_3d(&p.tm_dq, buf, chunk * 32, q_row_of(i), bh);
+                tma_reduce_add_3d(&p.tm_dq, stage, chunk * 32, q_row_of(i), bh);
                 tma_store_commit();
             }
         };
@@ -450,19 +447,11 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
             if (lane == 0) mbar_arrive(dq_empty);               // dP(i+1) may overwrite the columns now
             if (warp == D_WARP0) TL(16);
 
-            mbar_wait(ds_empty, i & 1);                         // dK(i), dQ(i) have finished reading dS(i)
-            if constexpr (CPW == 2) {
-                // first chunk through the (now dead) dS half: nothing of ours is pending on it
-                if (h * CPW < n_chunk) put_chunk(r[0], atom, h * CPW, i);
-            }
-            // last chunk through the dedicated buffer: its previous reduce must have been read
-            if (issuer) tma_store_wait_read<(CPW == 2) ? 1 : 0>();
-            named_bar_sync(bar_id, 128);
-            if (h * CPW + CPW - 1 < n_chunk) put_chunk(r[CPW - 1], stage, h * CPW + CPW - 1, i);
-            // hand the dS half back to the compute warps once the reduce out of it has been read
-            if (issuer) {
-                if constexpr (CPW == 2) tma_store_wait_read<1>();
-                mbar_arrive(atom_free);
+            // Only the drain warps ever wait for the reduce engine (they hold the tile in registers).
+#pragma unroll
+            for (int c = 0; c < CPW; ++c) {
+                const int chunk = h * CPW + c;
+                if (chunk < n_chunk) put_chunk(r[c], chunk, i);   // 16 KB box: [128 rows][32 fp32], 128B-swizzled
             }
             if (warp == D_WARP0) TL(17);
         }
