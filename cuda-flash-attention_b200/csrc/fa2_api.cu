@@ -251,77 +251,121 @@ struct HostJob {
     int mode;   // FA2_MODE_*
 };
 
+// One device's share [bh0, bh0+count) of the slabs, processed in chunks through two device buffer sets and
+// three streams so that the H2D copy of chunk c+1, the kernels of chunk c and the D2H copy of chunk c-1
+// overlap (PCIe is full duplex; the reference does malloc -> H2D -> kernel -> D2H -> free serially,
+// kernels/kernel_fa2_optimized.cu:371-421).
 int host_worker(const HostJob& job, int dev, int bh0, int count, float* ms_out, std::string* err_out) {
     auto run = [&]() -> int {
         FA2_CUDA(cudaSetDevice(dev));
         const size_t slab = static_cast<size_t>(job.S) * job.D;           // floats per (b,h)
-        const size_t n = slab * count, nl = static_cast<size_t>(job.S) * count;
-        const size_t tb = align_up(n * 4, 1024), lb = align_up(nl * 4, 1024);
         const bool fwd = job.mode != FA2_MODE_BACKWARD, bwd = job.mode != FA2_MODE_FORWARD;
-        // io arena: Q K V O LSE [dO dQ dK dV]
-        const size_t total = 4 * tb + lb + (bwd ? 4 * tb : 0);
+        // chunk size: ~8 chunks per device, but never so small that a chunk cannot fill the SMs
+        const int tiles = (job.S + 127) / 128;
+        int chunk_bh = (count + 7) / 8;
+        const int min_bh = (2 * 148 + tiles - 1) / tiles;
+        if (chunk_bh < min_bh) chunk_bh = min_bh;
+        if (chunk_bh > count) chunk_bh = count;
+        const int n_chunks = (count + chunk_bh - 1) / chunk_bh;
+        const size_t tb = align_up(slab * chunk_bh * 4, 1024), lb = align_up(static_cast<size_t>(job.S) * chunk_bh * 4, 1024);
+        const size_t set_bytes = 4 * tb + lb + (bwd ? 4 * tb : 0);       // Q K V O LSE [dO dQ dK dV]
         void* base = nullptr;
-        int rc = arena_reserve(g_io, dev, total, &base);
+        int rc = arena_reserve(g_io, dev, 2 * set_bytes, &base);
         if (rc) return rc;
-        uint8_t* b8 = static_cast<uint8_t*>(base);
-        float* dQ_ = nullptr; float* dK_ = nullptr; float* dV_ = nullptr; float* ddO = nullptr;
-        float* dQin = reinterpret_cast<float*>(b8);
-        float* dKin = reinterpret_cast<float*>(b8 + tb);
-        float* dVin = reinterpret_cast<float*>(b8 + 2 * tb);
-        float* dO_ = reinterpret_cast<float*>(b8 + 3 * tb);
-        float* dL = reinterpret_cast<float*>(b8 + 4 * tb);
-        if (bwd) {
-            ddO = reinterpret_cast<float*>(b8 + 4 * tb + lb);
-            dQ_ = reinterpret_cast<float*>(b8 + 5 * tb + lb);
-            dK_ = reinterpret_cast<float*>(b8 + 6 * tb + lb);
-            dV_ = reinterpret_cast<float*>(b8 + 7 * tb + lb);
-        }
-        cudaStream_t st;
-        FA2_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-        cudaEvent_t e0, e1;
-        FA2_CUDA(cudaEventCreate(&e0));
-        FA2_CUDA(cudaEventCreate(&e1));
-        const size_t off = static_cast<size_t>(bh0) * slab, offl = static_cast<size_t>(bh0) * job.S;
-        FA2_CUDA(cudaMemcpyAsync(dQin, job.Q + off, n * 4, cudaMemcpyHostToDevice, st));
-        FA2_CUDA(cudaMemcpyAsync(dKin, job.K + off, n * 4, cudaMemcpyHostToDevice, st));
-        FA2_CUDA(cudaMemcpyAsync(dVin, job.V + off, n * 4, cudaMemcpyHostToDevice, st));
-        if (job.mode == FA2_MODE_BACKWARD) {
-            FA2_CUDA(cudaMemcpyAsync(dO_, job.O_in + off, n * 4, cudaMemcpyHostToDevice, st));
-            FA2_CUDA(cudaMemcpyAsync(dL, job.LSE_in + offl, nl * 4, cudaMemcpyHostToDevice, st));
-        }
-        if (bwd) FA2_CUDA(cudaMemcpyAsync(ddO, job.dO + off, n * 4, cudaMemcpyHostToDevice, st));
         {   // keep one-time costs (module load, workspace growth) out of the timed region
             Prepared warm;
-            if ((rc = prepare(&warm, 1, count, job.S, job.D, job.precision, bwd))) return rc;
+            if ((rc = prepare(&warm, 1, chunk_bh, job.S, job.D, job.precision, bwd))) return rc;
             FA2_CUDA(warm_fwd());
             FA2_CUDA(warm_bwd());
         }
-        FA2_CUDA(cudaEventRecord(e0, st));
-        if (job.mode == FA2_MODE_FORWARD)
-            rc = fa2_forward(dQin, dKin, dVin, dO_, dL, 1, count, job.S, job.D, job.precision, st);
-        else if (job.mode == FA2_MODE_BACKWARD)
-            rc = fa2_backward(dQin, dKin, dVin, dO_, ddO, dL, dQ_, dK_, dV_, 1, count, job.S, job.D, job.precision, st);
-        else
-            rc = fa2_forward_backward(dQin, dKin, dVin, ddO, dO_, dL, dQ_, dK_, dV_, 1, count, job.S, job.D,
-                                      job.precision, st);
-        if (rc) return rc;
-        FA2_CUDA(cudaEventRecord(e1, st));
-        if (fwd) {
-            FA2_CUDA(cudaMemcpyAsync(job.O + off, dO_, n * 4, cudaMemcpyDeviceToHost, st));
-            FA2_CUDA(cudaMemcpyAsync(job.LSE + offl, dL, nl * 4, cudaMemcpyDeviceToHost, st));
+        cudaStream_t s_in, s_comp, s_out;
+        FA2_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+        FA2_CUDA(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
+        FA2_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+        cudaEvent_t ev_in[2], ev_comp[2], ev_out[2];
+        for (int i = 0; i < 2; ++i) {
+            FA2_CUDA(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
+            FA2_CUDA(cudaEventCreateWithFlags(&ev_comp[i], cudaEventDisableTiming));
+            FA2_CUDA(cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming));
         }
-        if (bwd) {
-            FA2_CUDA(cudaMemcpyAsync(job.dQ + off, dQ_, n * 4, cudaMemcpyDeviceToHost, st));
-            FA2_CUDA(cudaMemcpyAsync(job.dK + off, dK_, n * 4, cudaMemcpyDeviceToHost, st));
-            FA2_CUDA(cudaMemcpyAsync(job.dV + off, dV_, n * 4, cudaMemcpyDeviceToHost, st));
+        std::vector<cudaEvent_t> k0(n_chunks), k1(n_chunks);
+        for (int c = 0; c < n_chunks; ++c) {
+            FA2_CUDA(cudaEventCreate(&k0[c]));
+            FA2_CUDA(cudaEventCreate(&k1[c]));
         }
-        FA2_CUDA(cudaStreamSynchronize(st));
-        float ms = 0.f;
-        FA2_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-        *ms_out = ms;
-        cudaEventDestroy(e0);
-        cudaEventDestroy(e1);
-        cudaStreamDestroy(st);
+        for (int c = 0; c < n_chunks; ++c) {
+            const int set = c & 1;
+            const int cb0 = bh0 + c * chunk_bh;
+            const int cnt = (c == n_chunks - 1) ? (bh0 + count - cb0) : chunk_bh;
+            const size_t n = slab * cnt, nl = static_cast<size_t>(job.S) * cnt;
+            const size_t off = static_cast<size_t>(cb0) * slab, offl = static_cast<size_t>(cb0) * job.S;
+            uint8_t* b8 = static_cast<uint8_t*>(base) + set * set_bytes;
+            float* dQin = reinterpret_cast<float*>(b8);
+            float* dKin = reinterpret_cast<float*>(b8 + tb);
+            float* dVin = reinterpret_cast<float*>(b8 + 2 * tb);
+            float* dO_ = reinterpret_cast<float*>(b8 + 3 * tb);
+            float* dL = reinterpret_cast<float*>(b8 + 4 * tb);
+            float* ddO = bwd ? reinterpret_cast<float*>(b8 + 4 * tb + lb) : nullptr;
+            float* dQ_ = bwd ? reinterpret_cast<float*>(b8 + 5 * tb + lb) : nullptr;
+            float* dK_ = bwd ? reinterpret_cast<float*>(b8 + 6 * tb + lb) : nullptr;
+            float* dV_ = bwd ? reinterpret_cast<float*>(b8 + 7 * tb + lb) : nullptr;
+            // inputs of this buffer set were consumed by the kernels of chunk c-2
+            if (c >= 2) FA2_CUDA(cudaStreamWaitEvent(s_in, ev_comp[set], 0));
+            FA2_CUDA(cudaMemcpyAsync(dQin, job.Q + off, n * 4, cudaMemcpyHostToDevice, s_in));
+            FA2_CUDA(cudaMemcpyAsync(dKin, job.K + off, n * 4, cudaMemcpyHostToDevice, s_in));
+            FA2_CUDA(cudaMemcpyAsync(dVin, job.V + off, n * 4, cudaMemcpyHostToDevice, s_in));
+            if (job.mode == FA2_MODE_BACKWARD) {
+                FA2_CUDA(cudaMemcpyAsync(dO_, job.O_in + off, n * 4, cudaMemcpyHostToDevice, s_in));
+                FA2_CUDA(cudaMemcpyAsync(dL, job.LSE_in + offl, nl * 4, cudaMemcpyHostToDevice, s_in));
+            }
+            if (bwd) FA2_CUDA(cudaMemcpyAsync(ddO, job.dO + off, n * 4, cudaMemcpyHostToDevice, s_in));
+            FA2_CUDA(cudaEventRecord(ev_in[set], s_in));
+            // kernels: need the inputs, and the outputs of chunk c-2 must have left this buffer set
+            FA2_CUDA(cudaStreamWaitEvent(s_comp, ev_in[set], 0));
+            if (c >= 2) FA2_CUDA(cudaStreamWaitEvent(s_comp, ev_out[set], 0));
+            FA2_CUDA(cudaEventRecord(k0[c], s_comp));
+            if (job.mode == FA2_MODE_FORWARD)
+                rc = fa2_forward(dQin, dKin, dVin, dO_, dL, 1, cnt, job.S, job.D, job.precision, s_comp);
+            else if (job.mode == FA2_MODE_BACKWARD)
+                rc = fa2_backward(dQin, dKin, dVin, dO_, ddO, dL, dQ_, dK_, dV_, 1, cnt, job.S, job.D, job.precision, s_comp);
+            else
+                rc = fa2_forward_backward(dQin, dKin, dVin, ddO, dO_, dL, dQ_, dK_, dV_, 1, cnt, job.S, job.D,
+                                          job.precision, s_comp);
+            if (rc) return rc;
+            FA2_CUDA(cudaEventRecord(k1[c], s_comp));
+            FA2_CUDA(cudaEventRecord(ev_comp[set], s_comp));
+            FA2_CUDA(cudaStreamWaitEvent(s_out, ev_comp[set], 0));
+            if (fwd) {
+                FA2_CUDA(cudaMemcpyAsync(job.O + off, dO_, n * 4, cudaMemcpyDeviceToHost, s_out));
+                FA2_CUDA(cudaMemcpyAsync(job.LSE + offl, dL, nl * 4, cudaMemcpyDeviceToHost, s_out));
+            }
+            if (bwd) {
+                FA2_CUDA(cudaMemcpyAsync(job.dQ + off, dQ_, n * 4, cudaMemcpyDeviceToHost, s_out));
+                FA2_CUDA(cudaMemcpyAsync(job.dK + off, dK_, n * 4, cudaMemcpyDeviceToHost, s_out));
+                FA2_CUDA(cudaMemcpyAsync(job.dV + off, dV_, n * 4, cudaMemcpyDeviceToHost, s_out));
+            }
+            FA2_CUDA(cudaEventRecord(ev_out[set], s_out));
+        }
+        FA2_CUDA(cudaStreamSynchronize(s_in));
+        FA2_CUDA(cudaStreamSynchronize(s_comp));
+        FA2_CUDA(cudaStreamSynchronize(s_out));
+        float total_ms = 0.f;
+        for (int c = 0; c < n_chunks; ++c) {
+            float ms = 0.f;
+            FA2_CUDA(cudaEventElapsedTime(&ms, k0[c], k1[c]));
+            total_ms += ms;
+            cudaEventDestroy(k0[c]);
+            cudaEventDestroy(k1[c]);
+        }
+        *ms_out = total_ms;
+        for (int i = 0; i < 2; ++i) {
+            cudaEventDestroy(ev_in[i]);
+            cudaEventDestroy(ev_comp[i]);
+            cudaEventDestroy(ev_out[i]);
+        }
+        cudaStreamDestroy(s_in);
+        cudaStreamDestroy(s_comp);
+        cudaStreamDestroy(s_out);
         return FA2_OK;
     };
     int rc = run();
