@@ -181,8 +181,6 @@ int prepare(Prepared* pr, int B, int H, int S, int D, int precision, bool backwa
     return FA2_OK;
 }
 
-unsigned long long* g_timeline = nullptr;   // set by fa2_debug_set_timeline (debug builds)
-
 // optional per-kernel timing (fa2_profile_enable / fa2_profile_read)
 bool g_profile = false;
 struct ProfSpan { int kind; cudaEvent_t a, b; };
@@ -196,6 +194,8 @@ struct ProfScope {
         if (on) { cudaEventRecord(b, st); g_spans.push_back({kind, a, b}); }
     }
 };
+
+unsigned long long* g_timeline = nullptr;   // set by fa2_debug_set_timeline (debug builds)
 
 int run_cast(const Prepared& pr, const float* Q, const float* K, const float* V, cudaStream_t st) {
     ProfScope prof(0, st);
@@ -212,6 +212,7 @@ int run_fwd_main(const Prepared& pr, float* O, float* LSE, cudaStream_t st) {
     if ((rc = make_tmap_16(&p.tm_v, pr.work + pr.wl.off_v, pr.BH, pr.S, pr.DP, 128, pr.bf16))) return rc;
     p.O = O; p.LSE = LSE; p.BH = pr.BH; p.S = pr.S; p.D = pr.D;
     p.scale = pr.scale; p.scale_log2 = pr.scale_log2; p.bf16 = pr.bf16;
+    p.timeline = g_timeline;
     ProfScope prof(1, st);
     FA2_CUDA(launch_fwd(p, st));
     return FA2_OK;

@@ -23,6 +23,7 @@ struct FwdParams {
     float scale_log2;   // log2(e) / sqrt(D)
     float scale;        // 1 / sqrt(D)
     int bf16;
+    unsigned long long* timeline;   // debug builds (-DFA2_TIMELINE) only
 };
 
 struct BwdParams {

@@ -27,6 +27,19 @@ constexpr int NUM_THREADS = 384;        // 3 warpgroups; warps 10, 11 only donat
 constexpr int MMA_WARP = 8;
 constexpr int TMA_WARP = 9;
 constexpr float RESCALE_THRESHOLD = 8.0f;   // log2 units
+#ifndef FA2_POLY_EVERY
+#define FA2_POLY_EVERY 0
+#endif
+// 0: all exps on MUFU; k: one pair in every k groups of 4 goes through the FMA-pipe polynomial (2 -> 25 %).
+// Measured on B200 at config C (tools/fwd_variants.py, round-robin best of 6): k=0 1.810 ms, k=4 1.843, k=2 1.910,
+// k=1 1.967 -- the softmax warps are issue/latency-bound, not MUFU-bound, so the offload is off by default.
+constexpr int POLY_EVERY = FA2_POLY_EVERY;
+
+#ifdef FA2_TIMELINE
+#define TLF(slot) do { if (p.timeline && blockIdx.x == 0 && lane == 0 && j < 32) p.timeline[j * 32 + (slot)] = clock64(); } while (0)
+#else
+#define TLF(slot) do { } while (0)
+#endif
 
 template <int DP>
 struct FwdSmem {
@@ -188,11 +201,13 @@ fa2_fwd_kernel(const __grid_constant__ FwdParams p) {
                 for (int t = 0; t < n_qt; ++t) {
                     mbar_wait(&p_full[2 * t], j & 1);
                     tc_fence_after();
+                    TLF(t == 0 ? 0 : 2);
                     if (elect_one()) issue_pv(t, s, j == 0, std::integral_constant<int, 0>{});
                     __syncwarp();
                     mbar_wait(&p_full[2 * t + 1], j & 1);
                     if (j + 1 < n_kv && t == 0) mbar_wait(&k_full[s1], ph1);
                     tc_fence_after();
+                    TLF(t == 0 ? 1 : 3);
                     if (elect_one()) {
                         issue_pv(t, s, j == 0, std::integral_constant<int, 1>{});
                         if (t == n_qt - 1) umma_commit(&v_empty[s]);
@@ -228,6 +243,7 @@ fa2_fwd_kernel(const __grid_constant__ FwdParams p) {
         for (int j = 0; j < n_kv; ++j) {
             mbar_wait(&s_full[t], j & 1);
             tc_fence_after();
+            if ((warp & 3) == 0) TLF(t == 0 ? 8 : 12);
 
             uint32_t sr[4][32];
 #pragma unroll
@@ -287,7 +303,10 @@ fa2_fwd_kernel(const __grid_constant__ FwdParams p) {
                     const float2 x0 = __ffma2_rn(make_float2(__uint_as_float(sr[c][i]), __uint_as_float(sr[c][i + 1])), c2v, nmv);
                     const float2 x1 = __ffma2_rn(make_float2(__uint_as_float(sr[c][i + 2]), __uint_as_float(sr[c][i + 3])), c2v, nmv);
                     const float2 e0 = make_float2(ex2_approx(x0.x), ex2_approx(x0.y));
-                    const float2 e1 = make_float2(ex2_approx(x1.x), ex2_approx(x1.y));
+                    // every POLY_EVERY-th group computes its second pair with the FMA-pipe polynomial: MUFU and
+                    // the tensor core are co-bottlenecks at D=128 (both 2048 cycles per KV step)
+                    const float2 e1 = (POLY_EVERY > 0 && ((i >> 2) % (POLY_EVERY > 0 ? POLY_EVERY : 1)) == 0)
+                                          ? ex2_poly2(x1) : make_float2(ex2_approx(x1.x), ex2_approx(x1.y));
                     ls0 = __fadd2_rn(ls0, e0);
                     ls1 = __fadd2_rn(ls1, e1);
                     pk[i >> 1] = BF16 ? pack_bf16x2(e0.x, e0.y) : pack_half2(e0.x, e0.y);
@@ -299,6 +318,7 @@ fa2_fwd_kernel(const __grid_constant__ FwdParams p) {
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&p_full[2 * t + (c >> 1)]);
+                    if ((warp & 3) == 0) TLF((t == 0 ? 9 : 13) + (c >> 1));
                 }
             }
             l_run += (ls0.x + ls0.y) + (ls1.x + ls1.y);
