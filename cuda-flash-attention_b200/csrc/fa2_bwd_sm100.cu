@@ -476,7 +476,7 @@ cudaError_t launch_bwd(const BwdParams& p, cudaStream_t st) {
     const dim3 grid(static_cast<unsigned>(p.BH) * n_tiles);
     cudaError_t e;
     auto go = [&](auto kern, int smem) -> cudaError_t {
-        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t err = ensure_smem_optin(reinterpret_cast<const void*>(kern), smem);
         if (err != cudaSuccess) return err;
         kern<<<grid, NUM_THREADS, smem, st>>>(p);
         return cudaSuccess;

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>
+#include <mutex>
 
 namespace fa2 {
 
@@ -43,6 +44,29 @@ struct BwdParams {
     int bf16;
     unsigned long long* timeline;   // debug builds (-DFA2_TIMELINE) only: per-role clock64 stamps of CTA 0
 };
+
+// Opt a kernel in to > 48 KB of dynamic shared memory once per (kernel, device) instead of on every launch.
+inline cudaError_t ensure_smem_optin(const void* kern, int smem_bytes) {
+    static std::mutex mu;
+    static const void* kerns[16];
+    static bool done[16][64];
+    static int n = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(mu);
+    int k = 0;
+    while (k < n && kerns[k] != kern) ++k;
+    if (k == n) {
+        if (n == 16 || dev < 0 || dev >= 64) return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        kerns[n++] = kern;
+    }
+    if (dev < 0 || dev >= 64 || !done[k][dev]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) done[k][dev] = true;
+    }
+    return cudaSuccess;
+}
 
 // launchers (each returns a cudaError_t from the launch)
 cudaError_t launch_cast_qkv(const float* Q, const float* K, const float* V, void* Qh, void* Kh, void* Vh,
