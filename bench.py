@@ -282,11 +282,12 @@ def main():
     peak_burst, peak_sus, hbm, peak_src = measured_peaks()
     bwd_ms = kms[3] / max(kn[3], 1)
     fwd_ms = kms[1] / max(kn[1], 1)
-    traffic = None
+    traffic = traffic_fwd = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as fh:
-            traffic = json.load(fh).get("bwd_kernel_dram_bytes_per_launch")
+            tj = json.load(fh)
+            traffic, traffic_fwd = tj.get("bwd_kernel_dram_bytes_per_launch"), tj.get("fwd_kernel_dram_bytes_per_launch")
     achieved = f_bwd / (bwd_ms * 1e-3) / 1e12 if bwd_ms > 0 else None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -303,11 +304,19 @@ def main():
                    "bwd_kernel": achieved,
                    "frac_of_nominal_2250": {"fwd": f_fwd / (fwd_ms * 1e-3) / 1e12 / 2250 if fwd_ms else None,
                                             "bwd": achieved / 2250 if achieved else None}},
-        "roofline": {"bound": "tensor", "kernel": "fa2_bwd_kernel<128>", "achieved": achieved, "peak": peak_burst,
-                     "unit": "TFLOP/s", "frac": achieved / peak_burst if achieved else None, "traffic": traffic,
-                     "peak_source": f"MEASURED_PEAKS.json bf16_tflops (burst), {peak_src}",
-                     "frac_of_sustained": achieved / peak_sus if achieved else None,
-                     "fwd_kernel_frac": (f_fwd / (fwd_ms * 1e-3) / 1e12) / peak_burst if fwd_ms else None},
+        # the kernels are timed inside a long back-to-back loop (clocks under sw_power_cap, see "clocks"), so the
+        # denominator is the SUSTAINED measured cuBLAS bf16 peak; the burst figure is given beside it
+        "roofline": {"bound": "tensor", "kernel": "fa2_bwd_kernel<128,false> (dominant: %.0f %% of the step)" % (100.0 * bwd_ms / ms_step),
+                     "achieved": achieved, "peak": peak_sus, "unit": "TFLOP/s", "frac": achieved / peak_sus if achieved else None,
+                     "traffic": traffic,
+                     "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_src}); kernel timed inside the {args.steps}-step loop",
+                     "frac_of_burst_peak": achieved / peak_burst if achieved else None, "burst_peak": peak_burst,
+                     "algorithmic_flop_per_launch": f_bwd,
+                     "secondary_limit": "fp32 reduce-add of dQ into L2: 64 KB per 128x128 tile pair at ~24 B/clk/SM (tools/reduce_probe.cu)",
+                     "fwd_kernel": {"achieved": f_fwd / (fwd_ms * 1e-3) / 1e12 if fwd_ms else None,
+                                    "frac": (f_fwd / (fwd_ms * 1e-3) / 1e12) / peak_sus if fwd_ms else None,
+                                    "frac_of_burst_peak": (f_fwd / (fwd_ms * 1e-3) / 1e12) / peak_burst if fwd_ms else None,
+                                    "traffic": traffic_fwd}},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "fa2_host_forward_backward (C ABI, pinned host buffers)", "steps": args.e2e_steps},
     }
