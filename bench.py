@@ -288,6 +288,8 @@ def main():
         with open(tpath) as fh:
             tj = json.load(fh)
             traffic, traffic_fwd = tj.get("bwd_kernel_dram_bytes_per_launch"), tj.get("fwd_kernel_dram_bytes_per_launch")
+    if args.workload != "C":
+        traffic = traffic_fwd = None            # the ncu DRAM figures were captured on workload C only
     achieved = f_bwd / (bwd_ms * 1e-3) / 1e12 if bwd_ms > 0 else None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

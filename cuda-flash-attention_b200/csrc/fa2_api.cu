@@ -218,15 +218,19 @@ int run_fwd_main(const Prepared& pr, float* O, float* LSE, cudaStream_t st) {
     return FA2_OK;
 }
 
-int run_bwd_main(const Prepared& pr, const float* O, const float* dO, const float* LSE, float* dQ, float* dK,
-                 float* dV, cudaStream_t st) {
+int run_bwd_prepass(const Prepared& pr, const float* O, const float* dO, const float* LSE, float* dQ, int parts,
+                    cudaStream_t st) {
     float* delta = reinterpret_cast<float*>(pr.work + pr.wl.off_delta);
     float* lse2 = reinterpret_cast<float*>(pr.work + pr.wl.off_lse2);
-    {
     ProfScope prof(2, st);
     FA2_CUDA(launch_bwd_prepass(O, dO, LSE, pr.work + pr.wl.off_do, delta, lse2, dQ, pr.rows, pr.D, pr.DP, pr.bf16,
-                                st));
-    }
+                                parts, st));
+    return FA2_OK;
+}
+
+int run_bwd_main(const Prepared& pr, float* dQ, float* dK, float* dV, cudaStream_t st) {
+    float* delta = reinterpret_cast<float*>(pr.work + pr.wl.off_delta);
+    float* lse2 = reinterpret_cast<float*>(pr.work + pr.wl.off_lse2);
     BwdParams p{};
     int rc;
     if ((rc = make_tmap_16(&p.tm_q, pr.work + pr.wl.off_q, pr.BH, pr.S, pr.DP, 128, pr.bf16))) return rc;
@@ -544,7 +548,8 @@ int fa2_backward(const float* Q, const float* K, const float* V, const float* O,
     if (rc) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     if ((rc = run_cast(pr, Q, K, V, st))) return rc;
-    return run_bwd_main(pr, O, dO, LSE, dQ, dK, dV, st);
+    if ((rc = run_bwd_prepass(pr, O, dO, LSE, dQ, 3, st))) return rc;
+    return run_bwd_main(pr, dQ, dK, dV, st);
 }
 
 int fa2_forward_backward(const float* Q, const float* K, const float* V, const float* dO, float* O, float* LSE,
@@ -556,9 +561,12 @@ int fa2_forward_backward(const float* Q, const float* K, const float* V, const f
     int rc = prepare(&pr, B, H, S, D, precision, true);
     if (rc) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    // (Forking the dO cast / dQ zero-fill onto a side stream beside the forward was measured: no gain, the
+    // forward and the Q/K/V cast slow down by the same amount.)
     if ((rc = run_cast(pr, Q, K, V, st))) return rc;           // one 16-bit copy serves both passes
     if ((rc = run_fwd_main(pr, O, LSE, st))) return rc;
-    return run_bwd_main(pr, O, dO, LSE, dQ, dK, dV, st);
+    if ((rc = run_bwd_prepass(pr, O, dO, LSE, dQ, 3, st))) return rc;
+    return run_bwd_main(pr, dQ, dK, dV, st);
 }
 
 int fa2_host_forward(const float* Q, const float* K, const float* V, float* O, float* LSE, int B, int H, int S,

@@ -227,10 +227,10 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
                 });
             };
 
-            mbar_wait(kv_full, 0);
+            mbar_wait_spin(kv_full, 0);
             for (int i = 0; i < n_tiles; ++i) {
                 const int st = i % Q_STAGES;
-                mbar_wait(&q_full[st], (i / Q_STAGES) & 1);
+                mbar_wait_spin(&q_full[st], (i / Q_STAGES) & 1);
                 tc_fence_after();
                 TL(0);
                 if (elect_one()) {
@@ -239,7 +239,7 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
                 }
                 __syncwarp();
                 if (i > 0) {
-                    mbar_wait(ds_full, (i - 1) & 1);
+                    mbar_wait_spin(ds_full, (i - 1) & 1);
                     tc_fence_after();
                     TL(1);
                     if (elect_one()) {
@@ -250,16 +250,16 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
                         umma_commit(ds_empty);
                     }
                     __syncwarp();
-                    mbar_wait(dq_empty, (i - 1) & 1);          // dQ(i-1) drained out of TMEM
+                    mbar_wait_spin(dq_empty, (i - 1) & 1);          // dQ(i-1) drained out of TMEM
                 }
-                mbar_wait(do_full, i & 1);
+                mbar_wait_spin(do_full, i & 1);
                 tc_fence_after();
                 if (elect_one()) {
                     issue_dp();
                     umma_commit(dp_full);
                 }
                 __syncwarp();
-                mbar_wait(p_full, i & 1);
+                mbar_wait_spin(p_full, i & 1);
                 tc_fence_after();
                 TL(4);
                 if (elect_one()) {
@@ -270,7 +270,7 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
             }
             {
                 const int i = n_tiles - 1;
-                mbar_wait(ds_full, i & 1);
+                mbar_wait_spin(ds_full, i & 1);
                 tc_fence_after();
                 if (elect_one()) {
                     issue_dk(i % Q_STAGES, i == 0);

@@ -73,7 +73,7 @@ cudaError_t launch_cast_qkv(const float* Q, const float* K, const float* V, void
                             size_t rows, int D, int DP, int bf16, cudaStream_t st);
 cudaError_t launch_bwd_prepass(const float* O, const float* dO, const float* LSE, void* dOh, float* delta,
                                float* lse_log2, float* dQ_zero, size_t rows, int D, int DP, int bf16,
-                               cudaStream_t st);
+                               int parts /* 1: dO cast + dQ zero, 2: D_i + LSE, 3: both */, cudaStream_t st);
 cudaError_t launch_fwd(const FwdParams& p, cudaStream_t st);
 cudaError_t launch_bwd(const BwdParams& p, cudaStream_t st);
 cudaError_t warm_fwd();

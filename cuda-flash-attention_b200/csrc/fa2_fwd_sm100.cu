@@ -181,9 +181,9 @@ fa2_fwd_kernel(const __grid_constant__ FwdParams p) {
                 });
             };
 
-            mbar_wait(&k_full[0], 0);
+            mbar_wait_spin(&k_full[0], 0);
             for (int t = 0; t < n_qt; ++t) {
-                mbar_wait(&q_full[t], 0);
+                mbar_wait_spin(&q_full[t], 0);
                 tc_fence_after();
                 if (elect_one()) {
                     issue_qk(t, 0);
@@ -197,15 +197,15 @@ fa2_fwd_kernel(const __grid_constant__ FwdParams p) {
                 const uint32_t ph = (j / KV_STAGES) & 1;
                 const int s1 = (j + 1) % KV_STAGES;
                 const uint32_t ph1 = ((j + 1) / KV_STAGES) & 1;
-                mbar_wait(&v_full[s], ph);
+                mbar_wait_spin(&v_full[s], ph);
                 for (int t = 0; t < n_qt; ++t) {
-                    mbar_wait(&p_full[2 * t], j & 1);
+                    mbar_wait_spin(&p_full[2 * t], j & 1);
                     tc_fence_after();
                     TLF(t == 0 ? 0 : 2);
                     if (elect_one()) issue_pv(t, s, j == 0, std::integral_constant<int, 0>{});
                     __syncwarp();
-                    mbar_wait(&p_full[2 * t + 1], j & 1);
-                    if (j + 1 < n_kv && t == 0) mbar_wait(&k_full[s1], ph1);
+                    mbar_wait_spin(&p_full[2 * t + 1], j & 1);
+                    if (j + 1 < n_kv && t == 0) mbar_wait_spin(&k_full[s1], ph1);
                     tc_fence_after();
                     TLF(t == 0 ? 1 : 3);
                     if (elect_one()) {

@@ -45,7 +45,9 @@ cast_qkv_kernel(const float* __restrict__ Q, const float* __restrict__ K, const 
 }
 
 // One row per group of (D/8 <= 16) lanes: each lane handles 8 elements of the row.
-template <int LANES_PER_ROW>
+// PARTS bit 0: cast dO to 16 bit and zero-fill dQ (independent of the forward's outputs);
+// PARTS bit 1: D_i = rowsum(dO o O) and LSE -> log2 domain (need O / LSE).
+template <int LANES_PER_ROW, int PARTS>
 __global__ void __launch_bounds__(256)
 bwd_prepass_kernel(const float* __restrict__ O, const float* __restrict__ dO, const float* __restrict__ LSE,
                    uint4* __restrict__ dOh, float* __restrict__ delta, float* __restrict__ lse_log2,
@@ -66,25 +68,31 @@ bwd_prepass_kernel(const float* __restrict__ O, const float* __restrict__ dO, co
             if (col < D) {
                 const float4 a = __ldg(reinterpret_cast<const float4*>(dO + row * D + col));
                 const float4 b = __ldg(reinterpret_cast<const float4*>(dO + row * D + col + 4));
-                const float4 oa = __ldg(reinterpret_cast<const float4*>(O + row * D + col));
-                const float4 ob = __ldg(reinterpret_cast<const float4*>(O + row * D + col + 4));
-                acc = a.x * oa.x + a.y * oa.y + a.z * oa.z + a.w * oa.w + b.x * ob.x + b.y * ob.y + b.z * ob.z +
-                      b.w * ob.w;
-                out.x = pack16(a.x, a.y, bf16);
-                out.y = pack16(a.z, a.w, bf16);
-                out.z = pack16(b.x, b.y, bf16);
-                out.w = pack16(b.z, b.w, bf16);
-                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-                dQ[(row * D + col) >> 2] = z;
-                dQ[((row * D + col) >> 2) + 1] = z;
+                if (PARTS & 2) {
+                    const float4 oa = __ldg(reinterpret_cast<const float4*>(O + row * D + col));
+                    const float4 ob = __ldg(reinterpret_cast<const float4*>(O + row * D + col + 4));
+                    acc = a.x * oa.x + a.y * oa.y + a.z * oa.z + a.w * oa.w + b.x * ob.x + b.y * ob.y + b.z * ob.z +
+                          b.w * ob.w;
+                }
+                if (PARTS & 1) {
+                    out.x = pack16(a.x, a.y, bf16);
+                    out.y = pack16(a.z, a.w, bf16);
+                    out.z = pack16(b.x, b.y, bf16);
+                    out.w = pack16(b.z, b.w, bf16);
+                    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                    dQ[(row * D + col) >> 2] = z;
+                    dQ[((row * D + col) >> 2) + 1] = z;
+                }
             }
-            if (l < vec_per_row) dOh[row * vec_per_row + l] = out;
+            if ((PARTS & 1) && l < vec_per_row) dOh[row * vec_per_row + l] = out;
         }
+        if (PARTS & 2) {
 #pragma unroll
-        for (int off = LANES_PER_ROW / 2; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-        if (row < rows && l == 0) {
-            delta[row] = acc;
-            lse_log2[row] = LSE[row] * 1.4426950408889634f;
+            for (int off = LANES_PER_ROW / 2; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+            if (row < rows && l == 0) {
+                delta[row] = acc;
+                lse_log2[row] = LSE[row] * 1.4426950408889634f;
+            }
         }
     }
 }
@@ -103,21 +111,20 @@ cudaError_t launch_cast_qkv(const float* Q, const float* K, const float* V, void
 }
 
 cudaError_t launch_bwd_prepass(const float* O, const float* dO, const float* LSE, void* dOh, float* delta,
-                               float* lse_log2, float* dQ_zero, size_t rows, int D, int DP, int bf16,
+                               float* lse_log2, float* dQ_zero, size_t rows, int D, int DP, int bf16, int parts,
                                cudaStream_t st) {
     const int lanes = DP >> 3;                    // 8 (DP = 64) or 16 (DP = 128)
     const size_t rows_per_block = (256 / 32) * (32 / lanes);
     size_t blocks = (rows + rows_per_block - 1) / rows_per_block;
     if (blocks > 148 * 16) blocks = 148 * 16;
     if (blocks == 0) blocks = 1;
-    if (lanes == 8)
-        bwd_prepass_kernel<8><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
-            O, dO, LSE, static_cast<uint4*>(dOh), delta, lse_log2, reinterpret_cast<float4*>(dQ_zero), rows, D, DP,
-            bf16);
-    else
-        bwd_prepass_kernel<16><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
-            O, dO, LSE, static_cast<uint4*>(dOh), delta, lse_log2, reinterpret_cast<float4*>(dQ_zero), rows, D, DP,
-            bf16);
+    const unsigned g = static_cast<unsigned>(blocks);
+    uint4* dh = static_cast<uint4*>(dOh);
+    float4* dq = reinterpret_cast<float4*>(dQ_zero);
+#define FA2_PRE(L, P) bwd_prepass_kernel<L, P><<<g, 256, 0, st>>>(O, dO, LSE, dh, delta, lse_log2, dq, rows, D, DP, bf16)
+    if (lanes == 8) { if (parts == 1) FA2_PRE(8, 1); else if (parts == 2) FA2_PRE(8, 2); else FA2_PRE(8, 3); }
+    else            { if (parts == 1) FA2_PRE(16, 1); else if (parts == 2) FA2_PRE(16, 2); else FA2_PRE(16, 3); }
+#undef FA2_PRE
     return cudaGetLastError();
 }
 

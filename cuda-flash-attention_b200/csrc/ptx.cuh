@@ -148,6 +148,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// latency-critical waiters (the MMA issuer): poll without parking the warp
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+#ifdef FA2_MMA_SPIN
+    while (!mbar_test(bar, parity)) {
+    }
+#else
+    mbar_wait(bar, parity);
+#endif
+}
+
 // generic-proxy smem writes -> visible to the async proxy (TMA / UMMA operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

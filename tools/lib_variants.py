@@ -1,0 +1,35 @@
+#!/usr/bin/env python
+"""Round-robin timing (best of N rounds) of the forward and backward kernels of several library builds."""
+import ctypes
+import sys
+
+import torch
+
+B, H, S, D = 8, 32, 4096, 128
+q, k, v, g = (torch.randn(B, H, S, D, device="cuda") for _ in range(4))
+o = torch.empty_like(q); l = torch.empty(B, H, S, device="cuda")
+dq, dk, dv = (torch.empty_like(q) for _ in range(3))
+P = lambda t: ctypes.c_void_p(t.data_ptr())
+libs = [(p, ctypes.CDLL(p)) for p in sys.argv[1:]]
+best = {p: [1e9, 1e9] for p, _ in libs}
+
+
+def run(lib, n):
+    for _ in range(n):
+        lib.fa2_forward_backward(P(q), P(k), P(v), P(g), P(o), P(l), P(dq), P(dk), P(dv), B, H, S, D, 1, None)
+    torch.cuda.synchronize()
+
+
+for p, lib in libs:
+    lib.fa2_profile_enable(1)
+    run(lib, 2)
+for rnd in range(5):
+    for p, lib in libs:
+        ms = (ctypes.c_float * 4)(); n = (ctypes.c_int * 4)()
+        lib.fa2_profile_read(ms, n)
+        ms = (ctypes.c_float * 4)(); n = (ctypes.c_int * 4)()
+        run(lib, 4)
+        lib.fa2_profile_read(ms, n)
+        best[p][0] = min(best[p][0], ms[1] / n[1]); best[p][1] = min(best[p][1], ms[3] / n[3])
+for p, _ in libs:
+    print(f"{p.split('/')[-1]:24s} fwd {best[p][0]:.3f} ms   bwd {best[p][1]:.3f} ms")
