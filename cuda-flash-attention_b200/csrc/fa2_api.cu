@@ -265,9 +265,10 @@ int host_worker(const HostJob& job, int dev, int bh0, int count, float* ms_out, 
         FA2_CUDA(cudaSetDevice(dev));
         const size_t slab = static_cast<size_t>(job.S) * job.D;           // floats per (b,h)
         const bool fwd = job.mode != FA2_MODE_BACKWARD, bwd = job.mode != FA2_MODE_FORWARD;
-        // chunk size: ~8 chunks per device, but never so small that a chunk cannot fill the SMs
+        // chunk size: ~16 chunks per device (pipeline fill/drain = 2/16 of the transfer time), but never so small
+        // that a chunk cannot fill the SMs
         const int tiles = (job.S + 127) / 128;
-        int chunk_bh = (count + 7) / 8;
+        int chunk_bh = (count + 15) / 16;
         const int min_bh = (2 * 148 + tiles - 1) / tiles;
         if (chunk_bh < min_bh) chunk_bh = min_bh;
         if (chunk_bh > count) chunk_bh = count;
