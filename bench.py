@@ -194,6 +194,9 @@ def main():
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
+        # rank 0 must print exactly one JSON line on stdout: keep NCCL's version banner off it
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if args.gpus != world and rank == 0 and world > 1:
