@@ -251,9 +251,11 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
                     }
                     __syncwarp();
                     mbar_wait_spin(dq_empty, (i - 1) & 1);          // dQ(i-1) drained out of TMEM
+                    TL(2);
                 }
                 mbar_wait_spin(do_full, i & 1);
                 tc_fence_after();
+                TL(3);
                 if (elect_one()) {
                     issue_dp();
                     umma_commit(dp_full);
@@ -452,6 +454,7 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
             for (int c = 0; c < CPW; ++c) {
                 const int chunk = h * CPW + c;
                 if (chunk < n_chunk) put_chunk(r[c], chunk, i);   // 16 KB box: [128 rows][32 fp32], 128B-swizzled
+                if (warp == D_WARP0) TL(18 + c);
             }
             if (warp == D_WARP0) TL(17);
         }

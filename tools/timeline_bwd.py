@@ -25,7 +25,8 @@ torch.cuda.synchronize()
 t = tl.cpu().view(32, 32)
 names = {0: "MMA issue S", 1: "MMA ds_full(i-1) seen", 2: "MMA dq_empty(i-1) seen", 3: "MMA issue dP", 4: "MMA p_full seen/issue dV",
          8: "C  s_full seen", 9: "C  p_full arrive", 10: "C  dp_full seen", 11: "C  ds_full arrive",
-         15: "Dr dq_full seen", 16: "Dr dq_empty arrive", 17: "Dr staging done"}
+         15: "Dr dq_full seen", 16: "Dr dq_empty arrive", 17: "Dr staging done",
+         18: "Dr chunk0 issued", 19: "Dr chunk1 issued"}
 base = int(t[8, 0])
 n_it = min(32, (S + 127) // 128)
 for i in range(8, min(n_it, 13)):
