@@ -130,3 +130,12 @@ def test_host_api_chunked_pipeline_matches_device_api(U):
     assert np.array_equal(dK, U.host(dk)) and np.array_equal(dV, U.host(dv))
     assert U.maxerr(dQ, U.host(dq)) < 1e-5                                          # reduce-add order differs
     assert secs > 0
+
+
+def test_backward_bf16_operands_and_fp16_flag(U):
+    """The explicit bf16 flag (wider range, coarser mantissa) and the reference's `fp16` SHM-precision flag."""
+    Q, K, V, dO = U.randn_case((1, 2, 300, 128), seed=6)
+    tO, tL, tdQ, tdK, tdV = U.orc.attention_fp64(Q, K, V, dO)
+    for prec, tol in (("bf16", 3e-2), ("fp16", U.TOL_GRAD)):
+        dQ, dK, dV = U.gpu_backward(Q, K, V, tO.astype(np.float32), dO, tL.astype(np.float32), precision=prec)
+        assert max(U.maxerr(dQ, tdQ), U.maxerr(dK, tdK), U.maxerr(dV, tdV)) < tol, prec
