@@ -11,6 +11,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <initializer_list>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -146,6 +147,14 @@ int check_shape(int B, int H, int S, int D) {
         return fail(FA2_ERR_INVALID_ARGUMENT, "B*H too large");
     return FA2_OK;
 }
+// float4 loads/stores, TMA and the reduce-add all need 16-byte aligned tensors (any cudaMalloc / torch / CuPy
+// allocation is; an odd sub-view is not).
+bool aligned16(std::initializer_list<const void*> ptrs) {
+    for (const void* q : ptrs)
+        if (reinterpret_cast<uintptr_t>(q) & 15u) return false;
+    return true;
+}
+
 int check_precision(int precision) {
     if (precision != FA2_PRECISION_FP16 && precision != FA2_PRECISION_FP32 && precision != FA2_PRECISION_BF16)
         return fail(FA2_ERR_INVALID_ARGUMENT, "unknown precision %d", precision);
@@ -532,6 +541,7 @@ int fa2_release_workspaces(void) {
 int fa2_forward(const float* Q, const float* K, const float* V, float* O, float* LSE, int B, int H, int S, int D,
                 int precision, void* cuda_stream) {
     if (!Q || !K || !V || !O || !LSE) return fail(FA2_ERR_INVALID_ARGUMENT, "null pointer argument");
+    if (!aligned16({Q, K, V, O})) return fail(FA2_ERR_INVALID_ARGUMENT, "tensors must be 16-byte aligned");
     Prepared pr;
     int rc = prepare(&pr, B, H, S, D, precision, false);
     if (rc) return rc;
@@ -544,6 +554,7 @@ int fa2_backward(const float* Q, const float* K, const float* V, const float* O,
                  float* dQ, float* dK, float* dV, int B, int H, int S, int D, int precision, void* cuda_stream) {
     if (!Q || !K || !V || !O || !dO || !LSE || !dQ || !dK || !dV)
         return fail(FA2_ERR_INVALID_ARGUMENT, "null pointer argument");
+    if (!aligned16({Q, K, V, O, dO, dQ, dK, dV})) return fail(FA2_ERR_INVALID_ARGUMENT, "tensors must be 16-byte aligned");
     Prepared pr;
     int rc = prepare(&pr, B, H, S, D, precision, true);
     if (rc) return rc;
@@ -558,6 +569,7 @@ int fa2_forward_backward(const float* Q, const float* K, const float* V, const f
                          void* cuda_stream) {
     if (!Q || !K || !V || !O || !dO || !LSE || !dQ || !dK || !dV)
         return fail(FA2_ERR_INVALID_ARGUMENT, "null pointer argument");
+    if (!aligned16({Q, K, V, O, dO, dQ, dK, dV})) return fail(FA2_ERR_INVALID_ARGUMENT, "tensors must be 16-byte aligned");
     Prepared pr;
     int rc = prepare(&pr, B, H, S, D, precision, true);
     if (rc) return rc;

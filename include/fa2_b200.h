@@ -49,7 +49,9 @@ size_t fa2_workspace_bytes(int B, int H, int S, int D, int mode);
  *   D_computation_reduction_kernel_wrapper    kernels/f-attn2-backward.cu:514-528
  *   flash_attention2_backward_kernel_wrapper  kernels/f-attn2-backward.cu:491-512
  * as called by the harness (test_flash_attention2.py:278-289, :504-535).  All pointers are
- * device pointers on the current device, caller-owned.  Asynchronous on `cuda_stream`
+ * device pointers on the current device, caller-owned and 16-byte aligned.  The library keeps ONE scratch
+ * workspace per device: calls on the same device must be stream-ordered with respect to each other (one
+ * stream, or event dependencies); different devices are independent and may be driven from different threads.  Asynchronous on `cuda_stream`
  * (a cudaStream_t, NULL = default stream).  fa2_backward computes D_i = rowsum(dO*O) and
  * zero-fills dQ itself (the reference needs a separate launch and three fill(0)s).
  * ------------------------------------------------------------------------------------- */

@@ -109,3 +109,18 @@ def test_unsupported_head_dim_fails_loudly(U):
     x = np.zeros((1, 1, 16, 48), np.float32)
     with pytest.raises(fa2_b200.FA2Error):
         fa2_b200.run_flash_attention(x, x, x)
+
+
+def test_misaligned_tensor_is_rejected_not_miscomputed(U):
+    """float4 / TMA / reduce-add paths need 16-byte aligned tensors: an odd view must fail loudly."""
+    import ctypes
+    import torch
+    import fa2_b200
+    buf = torch.zeros(4 * 1 * 64 * 64 + 4, device="cuda")
+    q = buf[1:1 + 64 * 64]                                   # 4-byte offset into the allocation
+    ok = torch.zeros(1, 1, 64, 64, device="cuda")
+    lse = torch.zeros(1, 1, 64, device="cuda")
+    lib = fa2_b200.load()
+    rc = lib.fa2_forward(ctypes.c_void_p(q.data_ptr()), ctypes.c_void_p(ok.data_ptr()), ctypes.c_void_p(ok.data_ptr()),
+                         ctypes.c_void_p(ok.data_ptr()), ctypes.c_void_p(lse.data_ptr()), 1, 1, 64, 64, 1, None)
+    assert rc == 1 and b"16-byte" in lib.fa2_last_error()
