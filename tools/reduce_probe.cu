@@ -3,6 +3,8 @@
 //   mode 1: cp.reduce.async.bulk (1-D bulk reduce of 16 KB contiguous)
 //   mode 2: red.global.add.v4.f32 from registers (128 threads x 32 x 16 B)
 //   mode 3: red.global.add.f32 scalar, coalesced (warp covers 128 B)
+//   mode 6: mode 0 while warp 1 keeps TMA-LOADING 16 KB per reduced tile (like the Q / dO stream of fa2_bwd)
+//   mode 7: mode 0 while warps 1-3 load the same 16 KB per tile with cp.async (LDGSTS) instead of TMA
 // One CTA per SM, ITERS tiles each, distinct destination tiles (L2 resident).  Diagnostic tool only.
 #include <cstdio>
 #include <cuda.h>
@@ -35,6 +37,24 @@ __global__ void __launch_bounds__(128, 1) k(const __grid_constant__ Params p) {
                 tma_reduce_add_3d(&p.tm512, smem + (it & 1) * 16384, (it & 3) * 32, (t / 4) * 128, blockIdx.x);
                 tma_store_commit();
                 tma_store_wait_read<1>();
+            }
+        } else if (p.mode == 6 || p.mode == 7) {
+            if (threadIdx.x == 0) {
+                tma_reduce_add_3d(&p.tm, smem + (it & 1) * 16384, 0, t * 128, blockIdx.x);
+                tma_store_commit();
+                tma_store_wait_read<1>();
+            } else if (p.mode == 6 && threadIdx.x == 32) {
+                uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 49152);
+                if (it == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+                mbar_expect_tx(bar, 16384);
+                tma_load_3d(smem + 32768, &p.tm, bar, 0, ((t + 7) % tiles_per_cta) * 128, blockIdx.x);
+                mbar_wait(bar, it & 1);
+            } else if (p.mode == 7 && threadIdx.x >= 32) {
+                const float* src = base + (size_t)((t + 7) % tiles_per_cta) * 4096;
+                for (int q = threadIdx.x - 32; q < 1024; q += 96) {
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem + 32768 + q * 16)), "l"(src + q * 4) : "memory");
+                }
+                asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
             }
         } else if (p.mode == 1) {
             if (threadIdx.x == 0) {
@@ -97,12 +117,12 @@ int main() {
                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r2 != CUDA_SUCCESS) { printf("encode2 failed %d\n", (int)r2); return 2; }
     }
-    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 40000));
+    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 60000));
     for (int grid : {148, 16}) {
-        for (int mode = 0; mode < 6; ++mode) {
+        for (int mode : {0, 5, 6, 7}) {
             p.mode = mode;
-            k<<<grid, 128, 40000>>>(p); CK(cudaDeviceSynchronize());
-            k<<<grid, 128, 40000>>>(p); CK(cudaDeviceSynchronize());
+            k<<<grid, 128, 60000>>>(p); CK(cudaDeviceSynchronize());
+            k<<<grid, 128, 60000>>>(p); CK(cudaDeviceSynchronize());
             long long h[148]; CK(cudaMemcpy(h, cyc, grid * 8, cudaMemcpyDeviceToHost));
             double avg = 0; for (int i = 0; i < grid; ++i) avg += h[i]; avg /= grid;
             printf("grid %3d mode %d: %.0f cycles per iteration  (%.1f B/clk/SM)\n", grid, mode, avg / p.iters, (mode == 4 ? 2 : 1) * 16384.0 * p.iters / avg);
