@@ -195,8 +195,8 @@ def main():
     dist = None
     if world > 1:
         # rank 0 must print exactly one JSON line on stdout: keep NCCL's version banner off it
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # (NCCL logs to stdout by default, and WARN still prints the banner: send its log to stderr instead)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if args.gpus != world and rank == 0 and world > 1:
