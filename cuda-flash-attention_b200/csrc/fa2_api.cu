@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstring>
 #include <initializer_list>
+#include <chrono>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -219,6 +220,7 @@ int run_fwd_main(const Prepared& pr, float* O, float* LSE, cudaStream_t st) {
     if ((rc = make_tmap_16(&p.tm_q, pr.work + pr.wl.off_q, pr.BH, pr.S, pr.DP, 128, pr.bf16))) return rc;
     if ((rc = make_tmap_16(&p.tm_k, pr.work + pr.wl.off_k, pr.BH, pr.S, pr.DP, 128, pr.bf16))) return rc;
     if ((rc = make_tmap_16(&p.tm_v, pr.work + pr.wl.off_v, pr.BH, pr.S, pr.DP, 128, pr.bf16))) return rc;
+    if ((rc = make_tmap_f32(&p.tm_o, O, pr.BH, pr.S, pr.D))) return rc;
     p.O = O; p.LSE = LSE; p.BH = pr.BH; p.S = pr.S; p.D = pr.D;
     p.scale = pr.scale; p.scale_log2 = pr.scale_log2; p.bf16 = pr.bf16;
     p.timeline = g_timeline;
@@ -274,14 +276,25 @@ int host_worker(const HostJob& job, int dev, int bh0, int count, float* ms_out, 
         FA2_CUDA(cudaSetDevice(dev));
         const size_t slab = static_cast<size_t>(job.S) * job.D;           // floats per (b,h)
         const bool fwd = job.mode != FA2_MODE_BACKWARD, bwd = job.mode != FA2_MODE_FORWARD;
-        // chunk size: ~16 chunks per device (pipeline fill/drain = 2/16 of the transfer time), but never so small
-        // that a chunk cannot fill the SMs
+        // chunk size: ~16 chunks per device, but never so small that a chunk cannot fill the SMs.  PCIe is full
+        // duplex (measured 2 x 47 GB/s against 55 GB/s one way), so the job takes (bytes one way) / 47 GB/s plus
+        // whatever time only one direction is busy: the H2D of the first chunk and the D2H of the last.  Those two
+        // are cut to a quarter with a short ramp (1/4, 1/2 of a chunk) at both ends.
         const int tiles = (job.S + 127) / 128;
         int chunk_bh = (count + 15) / 16;
         const int min_bh = (2 * 148 + tiles - 1) / tiles;
         if (chunk_bh < min_bh) chunk_bh = min_bh;
         if (chunk_bh > count) chunk_bh = count;
-        const int n_chunks = (count + chunk_bh - 1) / chunk_bh;
+        std::vector<int> sizes;
+        {
+            int left = count;
+            const bool ramp = chunk_bh >= 4 && count >= 4 * chunk_bh;
+            const int r1 = chunk_bh / 4, r2 = chunk_bh / 2;
+            if (ramp) { sizes.push_back(r1); sizes.push_back(r2); left -= 2 * (r1 + r2); }
+            while (left > 0) { const int c = left < chunk_bh ? left : chunk_bh; sizes.push_back(c); left -= c; }
+            if (ramp) { sizes.push_back(r2); sizes.push_back(r1); }
+        }
+        const int n_chunks = static_cast<int>(sizes.size());
         const size_t tb = align_up(slab * chunk_bh * 4, 1024), lb = align_up(static_cast<size_t>(job.S) * chunk_bh * 4, 1024);
         const size_t set_bytes = 4 * tb + lb + (bwd ? 4 * tb : 0);       // Q K V O LSE [dO dQ dK dV]
         void* base = nullptr;
@@ -308,10 +321,19 @@ int host_worker(const HostJob& job, int dev, int bh0, int count, float* ms_out, 
             FA2_CUDA(cudaEventCreate(&k0[c]));
             FA2_CUDA(cudaEventCreate(&k1[c]));
         }
-        for (int c = 0; c < n_chunks; ++c) {
+        // FA2_HOST_TRACE=1: print when each chunk's copies and kernels ran (pipeline tuning aid)
+        static const bool trace = getenv("FA2_HOST_TRACE") != nullptr;
+        const auto wall0 = std::chrono::steady_clock::now();
+        std::vector<cudaEvent_t> tr;
+        if (trace) {
+            tr.resize(3 * n_chunks + 1);
+            for (auto& e : tr) FA2_CUDA(cudaEventCreate(&e));
+            FA2_CUDA(cudaEventRecord(tr[3 * n_chunks], s_in));
+        }
+        int cb0 = bh0;
+        for (int c = 0; c < n_chunks; cb0 += sizes[c], ++c) {
             const int set = c & 1;
-            const int cb0 = bh0 + c * chunk_bh;
-            const int cnt = (c == n_chunks - 1) ? (bh0 + count - cb0) : chunk_bh;
+            const int cnt = sizes[c];
             const size_t n = slab * cnt, nl = static_cast<size_t>(job.S) * cnt;
             const size_t off = static_cast<size_t>(cb0) * slab, offl = static_cast<size_t>(cb0) * job.S;
             uint8_t* b8 = static_cast<uint8_t*>(base) + set * set_bytes;
@@ -335,6 +357,7 @@ int host_worker(const HostJob& job, int dev, int bh0, int count, float* ms_out, 
             }
             if (bwd) FA2_CUDA(cudaMemcpyAsync(ddO, job.dO + off, n * 4, cudaMemcpyHostToDevice, s_in));
             FA2_CUDA(cudaEventRecord(ev_in[set], s_in));
+            if (trace) FA2_CUDA(cudaEventRecord(tr[3 * c], s_in));
             // kernels: need the inputs, and the outputs of chunk c-2 must have left this buffer set
             FA2_CUDA(cudaStreamWaitEvent(s_comp, ev_in[set], 0));
             if (c >= 2) FA2_CUDA(cudaStreamWaitEvent(s_comp, ev_out[set], 0));
@@ -360,10 +383,31 @@ int host_worker(const HostJob& job, int dev, int bh0, int count, float* ms_out, 
                 FA2_CUDA(cudaMemcpyAsync(job.dV + off, dV_, n * 4, cudaMemcpyDeviceToHost, s_out));
             }
             FA2_CUDA(cudaEventRecord(ev_out[set], s_out));
+            if (trace) {
+                FA2_CUDA(cudaEventRecord(tr[3 * c + 1], s_comp));
+                FA2_CUDA(cudaEventRecord(tr[3 * c + 2], s_out));
+            }
         }
+        const auto wall1 = std::chrono::steady_clock::now();
         FA2_CUDA(cudaStreamSynchronize(s_in));
         FA2_CUDA(cudaStreamSynchronize(s_comp));
         FA2_CUDA(cudaStreamSynchronize(s_out));
+        if (trace) {
+            const auto wall2 = std::chrono::steady_clock::now();
+            auto ms_of = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+            fprintf(stderr, "[fa2 host trace] dev %d: %d chunks, enqueue %.2f ms, drained at %.2f ms (wall, after setup)\n",
+                    dev, n_chunks, ms_of(wall0, wall1), ms_of(wall0, wall2));
+            for (int c = 0; c < n_chunks; ++c) {
+                float a = 0, b = 0, d = 0, k = 0;
+                cudaEventElapsedTime(&a, tr[3 * n_chunks], tr[3 * c]);
+                cudaEventElapsedTime(&b, tr[3 * n_chunks], tr[3 * c + 1]);
+                cudaEventElapsedTime(&d, tr[3 * n_chunks], tr[3 * c + 2]);
+                cudaEventElapsedTime(&k, k0[c], k1[c]);
+                fprintf(stderr, "  chunk %2d (%3d slabs): H2D done %7.2f  kernels done %7.2f (%.2f ms)  D2H done %7.2f\n", c,
+                        sizes[c], a, b, k, d);
+            }
+            for (auto& e : tr) cudaEventDestroy(e);
+        }
         float total_ms = 0.f;
         for (int c = 0; c < n_chunks; ++c) {
             float ms = 0.f;

@@ -18,6 +18,7 @@ struct FwdParams {
     CUtensorMap tm_q;   // 16-bit [BH][S][DP], box {64, 128, 1}, 128B swizzle
     CUtensorMap tm_k;
     CUtensorMap tm_v;
+    CUtensorMap tm_o;   // fp32 [BH][S][D], box {32, 128, 1}, 128B swizzle (store target)
     float* O;           // fp32 [BH][S][D]
     float* LSE;         // fp32 [BH][S] natural log
     int BH, S, D;

@@ -36,9 +36,12 @@ constexpr float RESCALE_THRESHOLD = 8.0f;   // log2 units
 constexpr int POLY_EVERY = FA2_POLY_EVERY;
 
 #ifdef FA2_TIMELINE
-#define TLF(slot) do { if (p.timeline && blockIdx.x == 0 && lane == 0 && j < 32) p.timeline[j * 32 + (slot)] = clock64(); } while (0)
+#define TLF(slot) do { if (p.timeline && w == 0 && lane == 0 && j < 32) p.timeline[j * 32 + (slot)] = clock64(); } while (0)
+// per-work-item marks: [1024 + 8 * w + k], k = 0 item picked up, 1 first S seen, 2 last O seen, 3 epilogue done, 4 SM id
+#define TLC(k) do { if (p.timeline) p.timeline[1024 + 8 * w + (k)] = clock64(); } while (0)
 #else
 #define TLF(slot) do { } while (0)
+#define TLC(k) do { } while (0)
 #endif
 
 template <int DP>
@@ -48,8 +51,10 @@ struct FwdSmem {
     static constexpr int OFF_Q = 0;                           // 2 tiles
     static constexpr int OFF_K = OFF_Q + 2 * TILE_BYTES;      // KV_STAGES tiles
     static constexpr int OFF_V = OFF_K + KV_STAGES * TILE_BYTES;
-    static constexpr int OFF_BAR = OFF_V + KV_STAGES * TILE_BYTES;
-    static constexpr int NUM_BARS = 2 + 4 * KV_STAGES + 2 + 4 + 2;
+    static constexpr int STAGE_BYTES = BM * 128;             // fp32 [128 rows][32 cols] O staging box, one per Q tile
+    static constexpr int OFF_STAGE = OFF_V + KV_STAGES * TILE_BYTES;
+    static constexpr int OFF_BAR = OFF_STAGE + 2 * STAGE_BYTES;
+    static constexpr int NUM_BARS = 2 + 4 * KV_STAGES + 2 + 4 + 2 + 1;
     static constexpr int OFF_TMEM_PTR = OFF_BAR + NUM_BARS * 8;
     static constexpr int BYTES = OFF_TMEM_PTR + 16;
     static constexpr int ALLOC = BYTES + 1024;                // slack for manual 1024-B alignment
@@ -75,21 +80,27 @@ fa2_fwd_kernel(const __grid_constant__ FwdParams p) {
     uint64_t* s_full = v_empty + KV_STAGES;        // [2]
     uint64_t* p_full = s_full + 2;                 // [2 tiles][2 halves of the KV columns]
     uint64_t* o_full = p_full + 4;                 // [2]
+    uint64_t* q_empty = o_full + 2;                // [1] every S of this work item has been computed
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + L::OFF_TMEM_PTR);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
+    // Persistent CTA: work item w = (bh, pair of Q tiles), taken round-robin so that the CTAs running at the same
+    // time walk the K/V of the same few heads (L2 reuse).  Every barrier parity below comes from running counters:
+    //   it        work items this CTA has started           (q_empty, Q tile 0, o_full[0])
+    //   n1        of those, the ones whose second Q tile exists (Q tile 1, o_full[1])
+    //   it * n_kv + j   KV ring position / tile 0 step;   n1 * n_kv + j   tile 1 step
     const int q_blocks = (p.S + 2 * BM - 1) / (2 * BM);
-    const int bh = blockIdx.x / q_blocks;
-    const int q_row0 = (blockIdx.x % q_blocks) * (2 * BM);
-    const int n_qt = (q_row0 + BM < p.S) ? 2 : 1;            // second tile may be fully out of range
+    const int n_work = p.BH * q_blocks;
     const int n_kv = (p.S + BN - 1) / BN;
+    auto tiles_of = [&](int w) { return ((w % q_blocks) * (2 * BM) + BM < p.S) ? 2 : 1; };
 
     if (warp == TMA_WARP && lane == 0) {
         tma_prefetch_desc(&p.tm_q);
         tma_prefetch_desc(&p.tm_k);
         tma_prefetch_desc(&p.tm_v);
+        tma_prefetch_desc(&p.tm_o);
     }
     if (warp == MMA_WARP) {
         if (lane == 0) {
@@ -106,6 +117,7 @@ fa2_fwd_kernel(const __grid_constant__ FwdParams p) {
                 mbar_init(&v_full[i], 1);
                 mbar_init(&v_empty[i], 1);
             }
+            mbar_init(q_empty, 1);
             fence_mbar_init();
         }
         __syncwarp();
@@ -119,34 +131,40 @@ fa2_fwd_kernel(const __grid_constant__ FwdParams p) {
     if (warp == TMA_WARP) {
         // ------------------------------------------------------------------ TMA producer
         setmaxnreg_dec<56>();
-        if (elect_one()) {
-            for (int t = 0; t < n_qt; ++t) {
-                mbar_expect_tx(&q_full[t], L::TILE_BYTES);
-                for (int a = 0; a < DP / 64; ++a)
-                    tma_load_3d(smem + L::OFF_Q + t * L::TILE_BYTES + a * L::ATOM_BYTES, &p.tm_q, &q_full[t],
-                                a * 64, q_row0 + t * BM, bh);
-            }
-        }
-        __syncwarp();
-        for (int j = 0; j < n_kv; ++j) {
-            const int s = j % KV_STAGES;
-            const uint32_t ph = (j / KV_STAGES) & 1;
-            mbar_wait(&k_empty[s], ph ^ 1);
+        int it = 0;
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+            const int bh = w / q_blocks, q_row0 = (w % q_blocks) * (2 * BM), n_qt = tiles_of(w);
+            mbar_wait(q_empty, (it & 1) ^ 1);          // the previous work item's last S has read the Q tiles
             if (elect_one()) {
-                mbar_expect_tx(&k_full[s], L::TILE_BYTES);
-                for (int a = 0; a < DP / 64; ++a)
-                    tma_load_3d(smem + L::OFF_K + s * L::TILE_BYTES + a * L::ATOM_BYTES, &p.tm_k, &k_full[s],
-                                a * 64, j * BN, bh);
+                for (int t = 0; t < n_qt; ++t) {
+                    mbar_expect_tx(&q_full[t], L::TILE_BYTES);
+                    for (int a = 0; a < DP / 64; ++a)
+                        tma_load_3d(smem + L::OFF_Q + t * L::TILE_BYTES + a * L::ATOM_BYTES, &p.tm_q, &q_full[t],
+                                    a * 64, q_row0 + t * BM, bh);
+                }
             }
             __syncwarp();
-            mbar_wait(&v_empty[s], ph ^ 1);
-            if (elect_one()) {
-                mbar_expect_tx(&v_full[s], L::TILE_BYTES);
-                for (int a = 0; a < DP / 64; ++a)
-                    tma_load_3d(smem + L::OFF_V + s * L::TILE_BYTES + a * L::ATOM_BYTES, &p.tm_v, &v_full[s],
-                                a * 64, j * BN, bh);
+            for (int j = 0; j < n_kv; ++j) {
+                const int g = it * n_kv + j;
+                const int s = g % KV_STAGES;
+                const uint32_t ph = (g / KV_STAGES) & 1;
+                mbar_wait(&k_empty[s], ph ^ 1);
+                if (elect_one()) {
+                    mbar_expect_tx(&k_full[s], L::TILE_BYTES);
+                    for (int a = 0; a < DP / 64; ++a)
+                        tma_load_3d(smem + L::OFF_K + s * L::TILE_BYTES + a * L::ATOM_BYTES, &p.tm_k, &k_full[s],
+                                    a * 64, j * BN, bh);
+                }
+                __syncwarp();
+                mbar_wait(&v_empty[s], ph ^ 1);
+                if (elect_one()) {
+                    mbar_expect_tx(&v_full[s], L::TILE_BYTES);
+                    for (int a = 0; a < DP / 64; ++a)
+                        tma_load_3d(smem + L::OFF_V + s * L::TILE_BYTES + a * L::ATOM_BYTES, &p.tm_v, &v_full[s],
+                                    a * 64, j * BN, bh);
+                }
+                __syncwarp();
             }
-            __syncwarp();
         }
     } else if (warp == MMA_WARP) {
         // ------------------------------------------------------------------ MMA issuer
@@ -181,46 +199,62 @@ fa2_fwd_kernel(const __grid_constant__ FwdParams p) {
                 });
             };
 
-            mbar_wait_spin(&k_full[0], 0);
-            for (int t = 0; t < n_qt; ++t) {
-                mbar_wait_spin(&q_full[t], 0);
-                tc_fence_after();
-                if (elect_one()) {
-                    issue_qk(t, 0);
-                    umma_commit(&s_full[t]);
-                    if (t == n_qt - 1) umma_commit(&k_empty[0]);   // K(0) is free once every S(0) has been computed
-                }
-                __syncwarp();
-            }
-            for (int j = 0; j < n_kv; ++j) {
-                const int s = j % KV_STAGES;
-                const uint32_t ph = (j / KV_STAGES) & 1;
-                const int s1 = (j + 1) % KV_STAGES;
-                const uint32_t ph1 = ((j + 1) / KV_STAGES) & 1;
-                mbar_wait_spin(&v_full[s], ph);
+            int it = 0, n1 = 0;
+            for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+                const int n_qt = tiles_of(w);
+                const int g0 = it * n_kv;                             // KV ring position of this item's step 0
+                // S(0) of both tiles.  The S / P columns are free (the last P V of the previous item was issued
+                // before this), so this overlaps the softmax warps' epilogue of the previous item.
+                mbar_wait_spin(&k_full[g0 % KV_STAGES], (g0 / KV_STAGES) & 1);
                 for (int t = 0; t < n_qt; ++t) {
-                    mbar_wait_spin(&p_full[2 * t], j & 1);
+                    mbar_wait_spin(&q_full[t], (t == 0 ? it : n1) & 1);
                     tc_fence_after();
-                    TLF(t == 0 ? 0 : 2);
-                    if (elect_one()) issue_pv(t, s, j == 0, std::integral_constant<int, 0>{});
-                    __syncwarp();
-                    mbar_wait_spin(&p_full[2 * t + 1], j & 1);
-                    if (j + 1 < n_kv && t == 0) mbar_wait_spin(&k_full[s1], ph1);
-                    tc_fence_after();
-                    TLF(t == 0 ? 1 : 3);
                     if (elect_one()) {
-                        issue_pv(t, s, j == 0, std::integral_constant<int, 1>{});
-                        if (t == n_qt - 1) umma_commit(&v_empty[s]);
-                        if (j + 1 < n_kv) {
-                            issue_qk(t, s1);
-                            umma_commit(&s_full[t]);
-                            if (t == n_qt - 1) umma_commit(&k_empty[s1]);
-                        } else {
-                            umma_commit(&o_full[t]);
+                        issue_qk(t, g0 % KV_STAGES);
+                        umma_commit(&s_full[t]);
+                        if (t == n_qt - 1) {
+                            umma_commit(&k_empty[g0 % KV_STAGES]);   // K(0) is free once every S(0) has been computed
+                            if (n_kv == 1) umma_commit(q_empty);
                         }
                     }
                     __syncwarp();
                 }
+                for (int j = 0; j < n_kv; ++j) {
+                    const int g = g0 + j;
+                    const int s = g % KV_STAGES;
+                    const uint32_t ph = (g / KV_STAGES) & 1;
+                    const int s1 = (g + 1) % KV_STAGES;
+                    const uint32_t ph1 = ((g + 1) / KV_STAGES) & 1;
+                    mbar_wait_spin(&v_full[s], ph);
+                    for (int t = 0; t < n_qt; ++t) {
+                        const uint32_t pp = ((t == 0 ? it : n1) * n_kv + j) & 1;
+                        mbar_wait_spin(&p_full[2 * t], pp);
+                        tc_fence_after();
+                        TLF(t == 0 ? 0 : 2);
+                        if (elect_one()) issue_pv(t, s, j == 0, std::integral_constant<int, 0>{});
+                        __syncwarp();
+                        mbar_wait_spin(&p_full[2 * t + 1], pp);
+                        if (j + 1 < n_kv && t == 0) mbar_wait_spin(&k_full[s1], ph1);
+                        tc_fence_after();
+                        TLF(t == 0 ? 1 : 3);
+                        if (elect_one()) {
+                            issue_pv(t, s, j == 0, std::integral_constant<int, 1>{});
+                            if (t == n_qt - 1) umma_commit(&v_empty[s]);
+                            if (j + 1 < n_kv) {
+                                issue_qk(t, s1);
+                                umma_commit(&s_full[t]);
+                                if (t == n_qt - 1) {
+                                    umma_commit(&k_empty[s1]);
+                                    if (j + 2 == n_kv) umma_commit(q_empty);   // that was the item's last S
+                                }
+                            } else {
+                                umma_commit(&o_full[t]);
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+                n1 += (n_qt == 2);
             }
         }
     } else if (warp >= 8) {
@@ -228,128 +262,156 @@ fa2_fwd_kernel(const __grid_constant__ FwdParams p) {
     } else {
         // ------------------------------------------------------------------ softmax + epilogue
         setmaxnreg_inc<224>();
-        if (warp < 4 * n_qt) {
         const int t = warp >> 2;
         const int row_in_tile = (warp & 3) * 32 + lane;
-        const int q_row = q_row0 + t * BM + row_in_tile;
         const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
         const uint32_t t_s = tmem_base + lane_addr + (t == 0 ? COL_S0 : COL_S1);
         const uint32_t t_o = tmem_base + lane_addr + (t == 0 ? COL_O0 : COL_O1);
         const float c2 = p.scale_log2;
+        uint8_t* stage = smem + L::OFF_STAGE + t * L::STAGE_BYTES;    // this warpgroup's 16 KB O staging buffer
+        const bool issuer = (warp & 3) == 0 && lane == 0;              // owns the warpgroup's TMA store groups
+        const uint32_t bar_id = 1 + 2 * t;
+        const int n_chunk = (p.D + 31) / 32;                           // real columns only (D = 32 under DP = 64)
 
-        float m_ref = -INFINITY;   // running reference max (raw score units)
-        float l_run = 0.0f;
-
-        for (int j = 0; j < n_kv; ++j) {
-            mbar_wait(&s_full[t], j & 1);
-            tc_fence_after();
-            if ((warp & 3) == 0) TLF(t == 0 ? 8 : 12);
-
-            uint32_t sr[4][32];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) tmem_ld32(t_s + c * 32, sr[c]);
-            tmem_wait_ld();
-
-            const int valid = p.S - j * BN;     // columns >= valid are padding in the last tile
-            if (valid < BN) {
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
-#pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (c * 32 + i >= valid) sr[c][i] = __float_as_uint(-INFINITY);
+        int mine = 0;                                                   // work items this warpgroup has processed
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+            if (t >= tiles_of(w)) continue;
+            const int bh = w / q_blocks, q_row0 = (w % q_blocks) * (2 * BM);
+            const int q_row = q_row0 + t * BM + row_in_tile;
+            const int step0 = mine * n_kv;
+#ifdef FA2_TIMELINE
+            if (threadIdx.x == 0 && p.timeline) {
+                uint32_t smid;
+                asm("mov.u32 %0, %%smid;" : "=r"(smid));
+                p.timeline[1024 + 8 * w + 4] = smid;
+                TLC(0);
             }
+#endif
 
-            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+            float m_ref = -INFINITY;   // running reference max (raw score units)
+            float l_run = 0.0f;
+
+            for (int j = 0; j < n_kv; ++j) {
+                mbar_wait(&s_full[t], (step0 + j) & 1);
+                tc_fence_after();
+                if ((warp & 3) == 0) TLF(t == 0 ? 8 : 12);
+                if (j == 0 && threadIdx.x == 0) TLC(1);
+
+                uint32_t sr[4][32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                mx0 = fmaxf(mx0, __uint_as_float(sr[0][i]));
-                mx1 = fmaxf(mx1, __uint_as_float(sr[1][i]));
-                mx2 = fmaxf(mx2, __uint_as_float(sr[2][i]));
-                mx3 = fmaxf(mx3, __uint_as_float(sr[3][i]));
-            }
-            const float m_new = fmaxf(fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)), m_ref);
+                for (int c = 0; c < 4; ++c) tmem_ld32(t_s + c * 32, sr[c]);
+                tmem_wait_ld();
 
-            if (j == 0) {
-                m_ref = m_new;
-            } else {
-                const bool need = (m_new - m_ref) * c2 > RESCALE_THRESHOLD;
-                if (__any_sync(0xffffffffu, need)) {
-                    // S(j) complete implies O += P V (j-1) complete (commits are ordered), so O is quiescent.
-                    const float alpha = ex2_approx((m_ref - m_new) * c2);
+                const int valid = p.S - j * BN;     // columns >= valid are padding in the last tile
+                if (valid < BN) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (c * 32 + i >= valid) sr[c][i] = __float_as_uint(-INFINITY);
+                }
+
+                float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    mx0 = fmaxf(mx0, __uint_as_float(sr[0][i]));
+                    mx1 = fmaxf(mx1, __uint_as_float(sr[1][i]));
+                    mx2 = fmaxf(mx2, __uint_as_float(sr[2][i]));
+                    mx3 = fmaxf(mx3, __uint_as_float(sr[3][i]));
+                }
+                const float m_new = fmaxf(fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)), m_ref);
+
+                if (j == 0) {
                     m_ref = m_new;
-                    l_run *= alpha;
+                } else {
+                    const bool need = (m_new - m_ref) * c2 > RESCALE_THRESHOLD;
+                    if (__any_sync(0xffffffffu, need)) {
+                        // S(j) complete implies O += P V (j-1) complete (commits are ordered), so O is quiescent.
+                        const float alpha = ex2_approx((m_ref - m_new) * c2);
+                        m_ref = m_new;
+                        l_run *= alpha;
 #pragma unroll
-                    for (int c = 0; c < DP / 32; ++c) {
-                        uint32_t orr[32];
-                        tmem_ld32(t_o + c * 32, orr);
-                        tmem_wait_ld();
+                        for (int c = 0; c < DP / 32; ++c) {
+                            uint32_t orr[32];
+                            tmem_ld32(t_o + c * 32, orr);
+                            tmem_wait_ld();
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) orr[i] = __float_as_uint(__uint_as_float(orr[i]) * alpha);
-                        tmem_st32(t_o + c * 32, orr);
+                            for (int i = 0; i < 32; ++i) orr[i] = __float_as_uint(__uint_as_float(orr[i]) * alpha);
+                            tmem_st32(t_o + c * 32, orr);
+                        }
                     }
                 }
+
+                // P = 2^(S*c2 - m*c2) with packed fp32x2 math, rounded to 16 bit and written over S (all of S is
+                // already in registers); handed to the MMA warp in two halves so P V can start early.
+                const float neg_m = -m_ref * c2;
+                const float2 c2v = make_float2(c2, c2), nmv = make_float2(neg_m, neg_m);
+                float2 ls0 = make_float2(0.f, 0.f), ls1 = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        const float2 x0 = __ffma2_rn(make_float2(__uint_as_float(sr[c][i]), __uint_as_float(sr[c][i + 1])), c2v, nmv);
+                        const float2 x1 = __ffma2_rn(make_float2(__uint_as_float(sr[c][i + 2]), __uint_as_float(sr[c][i + 3])), c2v, nmv);
+                        const float2 e0 = make_float2(ex2_approx(x0.x), ex2_approx(x0.y));
+                        // every POLY_EVERY-th group computes its second pair with the FMA-pipe polynomial (off)
+                        const float2 e1 = (POLY_EVERY > 0 && ((i >> 2) % (POLY_EVERY > 0 ? POLY_EVERY : 1)) == 0)
+                                              ? ex2_poly2(x1) : make_float2(ex2_approx(x1.x), ex2_approx(x1.y));
+                        ls0 = __fadd2_rn(ls0, e0);
+                        ls1 = __fadd2_rn(ls1, e1);
+                        pk[i >> 1] = BF16 ? pack_bf16x2(e0.x, e0.y) : pack_half2(e0.x, e0.y);
+                        pk[(i >> 1) + 1] = BF16 ? pack_bf16x2(e1.x, e1.y) : pack_half2(e1.x, e1.y);
+                    }
+                    tmem_st16(t_s + c * 16, pk);
+                    if (c & 1) {
+                        tmem_wait_st();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&p_full[2 * t + (c >> 1)]);
+                        if ((warp & 3) == 0) TLF((t == 0 ? 9 : 13) + (c >> 1));
+                    }
+                }
+                l_run += (ls0.x + ls0.y) + (ls1.x + ls1.y);
             }
 
-            // P = 2^(S*c2 - m*c2) with packed fp32x2 math, rounded to 16 bit and written over S (all of S is
-            // already in registers); handed to the MMA warp in two halves so P V can start early.
-            const float neg_m = -m_ref * c2;
-            const float2 c2v = make_float2(c2, c2), nmv = make_float2(neg_m, neg_m);
-            float2 ls0 = make_float2(0.f, 0.f), ls1 = make_float2(0.f, 0.f);
+            // epilogue: O / l -> 128B-swizzled fp32 staging tile -> TMA store (rows past S are clipped by the
+            // tensor map); LSE = ln(l) + m / sqrt(D).  The MMA warp is already computing S(0) of the next item.
+            mbar_wait(&o_full[t], mine & 1);
+            tc_fence_after();
+            if (threadIdx.x == 0) TLC(2);
+            const float inv_l = 1.0f / l_run;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                uint32_t pk[16];
+            for (int c = 0; c < DP / 32; ++c) {
+                if (c < n_chunk) {
+                    uint32_t orr[32];
+                    tmem_ld32(t_o + c * 32, orr);
+                    tmem_wait_ld();
+                    if (issuer) tma_store_wait_read<0>();       // the previous store out of the buffer has been read
+                    named_bar_sync(bar_id, 128);
 #pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    const float2 x0 = __ffma2_rn(make_float2(__uint_as_float(sr[c][i]), __uint_as_float(sr[c][i + 1])), c2v, nmv);
-                    const float2 x1 = __ffma2_rn(make_float2(__uint_as_float(sr[c][i + 2]), __uint_as_float(sr[c][i + 3])), c2v, nmv);
-                    const float2 e0 = make_float2(ex2_approx(x0.x), ex2_approx(x0.y));
-                    // every POLY_EVERY-th group computes its second pair with the FMA-pipe polynomial: MUFU and
-                    // the tensor core are co-bottlenecks at D=128 (both 2048 cycles per KV step)
-                    const float2 e1 = (POLY_EVERY > 0 && ((i >> 2) % (POLY_EVERY > 0 ? POLY_EVERY : 1)) == 0)
-                                          ? ex2_poly2(x1) : make_float2(ex2_approx(x1.x), ex2_approx(x1.y));
-                    ls0 = __fadd2_rn(ls0, e0);
-                    ls1 = __fadd2_rn(ls1, e1);
-                    pk[i >> 1] = BF16 ? pack_bf16x2(e0.x, e0.y) : pack_half2(e0.x, e0.y);
-                    pk[(i >> 1) + 1] = BF16 ? pack_bf16x2(e1.x, e1.y) : pack_half2(e1.x, e1.y);
-                }
-                tmem_st16(t_s + c * 16, pk);
-                if (c & 1) {
-                    tmem_wait_st();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&p_full[2 * t + (c >> 1)]);
-                    if ((warp & 3) == 0) TLF((t == 0 ? 9 : 13) + (c >> 1));
-                }
-            }
-            l_run += (ls0.x + ls0.y) + (ls1.x + ls1.y);
-        }
-
-        // epilogue: O / l -> fp32 global, LSE = ln(l) + m / sqrt(D)
-        mbar_wait(&o_full[t], 0);
-        tc_fence_after();
-        const float inv_l = 1.0f / l_run;
-        const bool row_ok = q_row < p.S;
-        float* o_row = p.O + (static_cast<size_t>(bh) * p.S + (row_ok ? q_row : 0)) * p.D;
-#pragma unroll
-        for (int c = 0; c < DP / 32; ++c) {
-            uint32_t orr[32];
-            tmem_ld32(t_o + c * 32, orr);
-            tmem_wait_ld();
-            if (row_ok && c * 32 < p.D) {
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    float4 v4;
-                    v4.x = __uint_as_float(orr[i]) * inv_l;
-                    v4.y = __uint_as_float(orr[i + 1]) * inv_l;
-                    v4.z = __uint_as_float(orr[i + 2]) * inv_l;
-                    v4.w = __uint_as_float(orr[i + 3]) * inv_l;
-                    *reinterpret_cast<float4*>(o_row + c * 32 + i) = v4;
+                    for (int q4 = 0; q4 < 8; ++q4) {
+                        float4 v4;
+                        v4.x = __uint_as_float(orr[q4 * 4]) * inv_l;
+                        v4.y = __uint_as_float(orr[q4 * 4 + 1]) * inv_l;
+                        v4.z = __uint_as_float(orr[q4 * 4 + 2]) * inv_l;
+                        v4.w = __uint_as_float(orr[q4 * 4 + 3]) * inv_l;
+                        *reinterpret_cast<float4*>(stage + swz128(row_in_tile, q4)) = v4;
+                    }
+                    fence_proxy_async_smem();
+                    named_bar_sync(bar_id + 1, 128);
+                    if (issuer) {
+                        tma_store_3d(&p.tm_o, stage, c * 32, q_row0 + t * BM, bh);
+                        tma_store_commit();
+                    }
+                    if (threadIdx.x == 0 && c < 3) TLC(5 + c);
                 }
             }
+            if (q_row < p.S) p.LSE[static_cast<size_t>(bh) * p.S + q_row] = m_ref * p.scale + logf(l_run);
+            if (threadIdx.x == 0) TLC(3);
+            ++mine;
         }
-        if (row_ok)
-            p.LSE[static_cast<size_t>(bh) * p.S + q_row] = m_ref * p.scale + logf(l_run);
-        }
+        if (issuer) tma_store_wait<0>();                        // global writes done before the CTA retires
     }
 
     tc_fence_before();
@@ -365,7 +427,17 @@ fa2_fwd_kernel(const __grid_constant__ FwdParams p) {
 cudaError_t launch_fwd(const FwdParams& p, cudaStream_t st) {
     const int DP = padded_head_dim(p.D);
     const int q_blocks = (p.S + 2 * BM - 1) / (2 * BM);
-    const dim3 grid(static_cast<unsigned>(p.BH) * q_blocks);
+    // persistent: one CTA per SM (or fewer when there is less work), each walks its share of the work items
+    static int sm_count[64] = {0};
+    int dev = 0;
+    cudaError_t e0 = cudaGetDevice(&dev);
+    if (e0 != cudaSuccess) return e0;
+    if (dev < 64 && sm_count[dev] == 0 &&
+        (e0 = cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess)
+        return e0;
+    const long long n_work = static_cast<long long>(p.BH) * q_blocks;
+    const int n_sm = dev < 64 ? sm_count[dev] : 148;
+    const dim3 grid(static_cast<unsigned>(n_work < n_sm ? n_work : n_sm));
     cudaError_t e;
     auto go = [&](auto kern, int smem) -> cudaError_t {
         cudaError_t err = ensure_smem_optin(reinterpret_cast<const void*>(kern), smem);

@@ -132,6 +132,20 @@ def test_host_api_chunked_pipeline_matches_device_api(U):
     assert secs > 0
 
 
+def test_host_api_ramped_chunks_match_device_api(U):
+    """48 slabs of S=4096 are streamed as 2 + 5 + 10 + 10 + 10 + 4 + 5 + 2 (short chunks at both ends keep the
+    one-directional PCIe phases short); every slab must land where the one-shot device path puts it."""
+    import torch
+    import fa2_b200
+    Q, K, V, dO = U.randn_case((1, 48, 4096, 64), seed=23)
+    (O, L, dQ, dK, dV), _ = fa2_b200.run_flash_attention(Q, K, V, dO=dO, mode="forward_backward")
+    o, l, dq, dk, dv = fa2_b200.forward_backward(*(U.dev(x) for x in (Q, K, V, dO)))
+    torch.cuda.synchronize()
+    assert np.array_equal(O, U.host(o)) and np.array_equal(L, U.host(l))
+    assert np.array_equal(dK, U.host(dk)) and np.array_equal(dV, U.host(dv))
+    assert U.maxerr(dQ, U.host(dq)) < 1e-5
+
+
 def test_backward_bf16_operands_and_fp16_flag(U):
     """The explicit bf16 flag (wider range, coarser mantissa) and the reference's `fp16` SHM-precision flag."""
     Q, K, V, dO = U.randn_case((1, 2, 300, 128), seed=6)
