@@ -249,6 +249,8 @@ int run_bwd_main(const Prepared& pr, float* dQ, float* dK, float* dV, cudaStream
     if ((rc = make_tmap_16(&p.tm_v, pr.work + pr.wl.off_v, pr.BH, pr.S, pr.DP, 128, pr.bf16))) return rc;
     if ((rc = make_tmap_16(&p.tm_do, pr.work + pr.wl.off_do, pr.BH, pr.S, pr.DP, 128, pr.bf16))) return rc;
     if ((rc = make_tmap_f32(&p.tm_dq, dQ, pr.BH, pr.S, pr.D))) return rc;
+    if ((rc = make_tmap_f32(&p.tm_dk, dK, pr.BH, pr.S, pr.D))) return rc;
+    if ((rc = make_tmap_f32(&p.tm_dv, dV, pr.BH, pr.S, pr.D))) return rc;
     p.lse_log2 = lse2; p.delta = delta; p.dQ = dQ; p.dK = dK; p.dV = dV;
     p.BH = pr.BH; p.S = pr.S; p.D = pr.D; p.scale = pr.scale; p.scale_log2 = pr.scale_log2; p.bf16 = pr.bf16;
     p.timeline = g_timeline;

@@ -40,9 +40,12 @@ constexpr int Q_STAGES = 2;
 
 // Debug timeline (only with -DFA2_TIMELINE): lane 0 of a role stamps clock64 into slot `slot` of iteration i.
 #ifdef FA2_TIMELINE
-#define TL(slot) do { if (p.timeline && blockIdx.x == 0 && lane == 0 && i < 32) p.timeline[i * 32 + (slot)] = clock64(); } while (0)
+#define TL(slot) do { if (p.timeline && w == 0 && lane == 0 && i < 32) p.timeline[i * 32 + (slot)] = clock64(); } while (0)
+// per-work-item marks: [1024 + 8 * w + k], k = 0 item picked up, 1 first S seen, 2 dK/dV complete, 3 epilogue done, 4 SM id
+#define TLC(k) do { if (p.timeline) p.timeline[1024 + 8 * w + (k)] = clock64(); } while (0)
 #else
 #define TL(slot) do { } while (0)
+#define TLC(k) do { } while (0)
 #endif
 
 template <int DP>
@@ -86,6 +89,7 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
     uint64_t* dq_full = bars + 12;
     uint64_t* dq_empty = bars + 13;
     uint64_t* dkdv_full = bars + 14;
+    uint64_t* kv_empty = bars + 15;   // the item's last dQ / dP have read the K / V tiles
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + L::OFF_TMEM_PTR);
     float* lse_s = reinterpret_cast<float*>(smem + L::OFF_LSE);
     float* delta_s = reinterpret_cast<float*>(smem + L::OFF_DELTA);
@@ -93,20 +97,23 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
+    // Persistent CTA: work item w = (bh, KV tile), taken round-robin so that the CTAs running at the same time
+    // work on neighbouring KV tiles of the same few heads (Q / dO reuse in L2).  All items have n_tiles steps, so
+    // every per-step barrier parity comes from the running step count G = it * n_tiles + i and every per-item
+    // parity from it (items this CTA has started).
     const int n_tiles = (p.S + BT - 1) / BT;       // same count for KV and Q tiles
-    const int bh = blockIdx.x / n_tiles;
-    const int kv_tile = blockIdx.x % n_tiles;
-    const int kv_row0 = kv_tile * BT;
-    // Every CTA of a (b,h) slab walks the Q tiles in a different rotation, so that at any moment the
+    const int n_work = p.BH * n_tiles;
+    // Every KV tile of a (b,h) slab walks the Q tiles in a different rotation, so that at any moment the
     // concurrently running CTAs reduce-add into DIFFERENT dQ tiles (no same-address contention in L2).
-    auto q_row_of = [&](int i) { int t = i + kv_tile; if (t >= n_tiles) t -= n_tiles; return t * BT; };
-
+    auto q_row_at = [&](int kv_tile, int i) { int t = i + kv_tile; if (t >= n_tiles) t -= n_tiles; return t * BT; };
     if (warp == TMA_WARP && lane == 0) {
         tma_prefetch_desc(&p.tm_q);
         tma_prefetch_desc(&p.tm_k);
         tma_prefetch_desc(&p.tm_v);
         tma_prefetch_desc(&p.tm_do);
         tma_prefetch_desc(&p.tm_dq);
+        tma_prefetch_desc(&p.tm_dk);
+        tma_prefetch_desc(&p.tm_dv);
     }
     if (warp == MMA_WARP) {
         if (lane == 0) {
@@ -126,6 +133,7 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
             mbar_init(dq_full, 1);
             mbar_init(dq_empty, 8);           // one arrive per drain warp
             mbar_init(dkdv_full, 1);
+            mbar_init(kv_empty, 1);
             fence_mbar_init();
         }
         __syncwarp();
@@ -139,6 +147,11 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
     if (warp == TMA_WARP) {
         // ------------------------------------------------------------------ producer
         setmaxnreg_dec<40>();
+        int it = 0;
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+        const int bh = w / n_tiles, kv_tile = w % n_tiles, kv_row0 = kv_tile * BT;
+        auto q_row_of = [&](int i) { return q_row_at(kv_tile, i); };
+        mbar_wait(kv_empty, (it & 1) ^ 1);                     // previous item's MMAs are done with K / V
         if (elect_one()) {
             mbar_expect_tx(kv_full, 2 * L::TILE);
             for (int a = 0; a < DP / 64; ++a) {
@@ -146,9 +159,11 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
                 tma_load_3d(smem + L::OFF_V + a * ATOM, &p.tm_v, kv_full, a * 64, kv_row0, bh);
             }
         }
+        __syncwarp();
         for (int i = 0; i < n_tiles; ++i) {
-            const int s = i % Q_STAGES;
-            const uint32_t ph = (i / Q_STAGES) & 1;
+            const int G = it * n_tiles + i;
+            const int s = G % Q_STAGES;
+            const uint32_t ph = (G / Q_STAGES) & 1;
             mbar_wait(&q_empty[s], ph ^ 1);
             if (elect_one()) {
                 mbar_expect_tx(&q_full[s], L::TILE);
@@ -168,13 +183,14 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
             __syncwarp();
             if (elect_one()) mbar_arrive(&q_full[s]);           // LSE / D_i staged (the Q tile itself lands via TMA)
             __syncwarp();
-            mbar_wait(do_empty, (i & 1) ^ 1);
+            mbar_wait(do_empty, (G & 1) ^ 1);
             if (elect_one()) {
                 mbar_expect_tx(do_full, L::TILE);
                 for (int a = 0; a < DP / 64; ++a)
                     tma_load_3d(smem + L::OFF_DO + a * ATOM, &p.tm_do, do_full, a * 64, q_row_of(i), bh);
             }
             __syncwarp();
+        }
         }
     } else if (warp == MMA_WARP) {
         // ------------------------------------------------------------------ MMA issuer
@@ -227,33 +243,39 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
                 });
             };
 
-            mbar_wait_spin(kv_full, 0);
+            int it = 0;
+            for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+            const int G0 = it * n_tiles;
+            mbar_wait_spin(kv_full, it & 1);
             for (int i = 0; i < n_tiles; ++i) {
-                const int st = i % Q_STAGES;
-                mbar_wait_spin(&q_full[st], (i / Q_STAGES) & 1);
+                const int G = G0 + i;
+                const int st = G % Q_STAGES;
+                mbar_wait_spin(&q_full[st], (G / Q_STAGES) & 1);
                 tc_fence_after();
                 TL(0);
                 if (elect_one()) {
-                    issue_s(st);                               // dV(i-1) was issued before, so P^T(i-1) is consumed
+                    issue_s(st);                               // dV(G-1) was issued before, so P^T(G-1) is consumed
                     umma_commit(s_full);
                 }
                 __syncwarp();
                 if (i > 0) {
-                    mbar_wait_spin(ds_full, (i - 1) & 1);
+                    mbar_wait_spin(ds_full, (G - 1) & 1);
                     tc_fence_after();
                     TL(1);
                     if (elect_one()) {
                         issue_dq();                            // dQ(i-1) over the dead dP(i-1)
                         umma_commit(dq_full);
-                        issue_dk((i - 1) % Q_STAGES, i == 1);  // dK += dS(i-1)^T Q(i-1)
-                        umma_commit(&q_empty[(i - 1) % Q_STAGES]);
+                        issue_dk((G - 1) % Q_STAGES, i == 1);  // dK += dS(i-1)^T Q(i-1)
+                        umma_commit(&q_empty[(G - 1) % Q_STAGES]);
                         umma_commit(ds_empty);
                     }
                     __syncwarp();
-                    mbar_wait_spin(dq_empty, (i - 1) & 1);          // dQ(i-1) drained out of TMEM
+                }
+                if (G > 0) {
+                    mbar_wait_spin(dq_empty, (G - 1) & 1);          // dQ(G-1) drained out of TMEM (i == 0: previous item's last)
                     TL(2);
                 }
-                mbar_wait_spin(do_full, i & 1);
+                mbar_wait_spin(do_full, G & 1);
                 tc_fence_after();
                 TL(3);
                 if (elect_one()) {
@@ -261,7 +283,7 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
                     umma_commit(dp_full);
                 }
                 __syncwarp();
-                mbar_wait_spin(p_full, i & 1);
+                mbar_wait_spin(p_full, G & 1);
                 tc_fence_after();
                 TL(4);
                 if (elect_one()) {
@@ -271,16 +293,20 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
                 __syncwarp();
             }
             {
-                const int i = n_tiles - 1;
-                mbar_wait_spin(ds_full, i & 1);
+                const int i = n_tiles - 1, G = G0 + i;
+                mbar_wait_spin(ds_full, G & 1);
                 tc_fence_after();
                 if (elect_one()) {
-                    issue_dk(i % Q_STAGES, i == 0);
+                    issue_dk(G % Q_STAGES, i == 0);
                     issue_dq();
                     umma_commit(dq_full);
                     umma_commit(dkdv_full);
+                    umma_commit(&q_empty[G % Q_STAGES]);       // the next item reuses the Q stage, the dS tile
+                    umma_commit(ds_empty);                     // and the K / V tiles
+                    umma_commit(kv_empty);
                 }
                 __syncwarp();
+            }
             }
         }
     } else if (warp < D_WARP0) {
@@ -293,15 +319,32 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
         const uint32_t tDP = tmem_base + lane_addr + COL_DP + h * 64;
         const float2 c2v = make_float2(p.scale_log2, p.scale_log2);
         uint8_t* ds_atom = smem + L::OFF_DS + h * ATOM;        // Q columns [64h, 64h+64) = swizzle atom h
+        const bool issuer = ((warp & 3) == 0) && lane == 0;    // owns this warpgroup's dK / dV store groups
+        const uint32_t ep_bar = 5 + 2 * h;                      // named barriers private to this warpgroup
+        const int n_chunk = (p.D + 31) / 32;                   // real columns only (D = 32 under DP = 64)
 
+        int it = 0;
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+        const int bh = w / n_tiles, kv_row0 = (w % n_tiles) * BT;
+        const int G0 = it * n_tiles;
+#ifdef FA2_TIMELINE
+        if (threadIdx.x == 0 && p.timeline) {
+            uint32_t smid;
+            asm("mov.u32 %0, %%smid;" : "=r"(smid));
+            p.timeline[1024 + 8 * w + 4] = smid;
+            TLC(0);
+        }
+#endif
         for (int i = 0; i < n_tiles; ++i) {
-            const int st = i % Q_STAGES;
+            const int G = G0 + i;
+            const int st = G % Q_STAGES;
             const float4* lse_t = reinterpret_cast<const float4*>(lse_s + st * BT + h * 64);
             const float4* dl_t = reinterpret_cast<const float4*>(delta_s + st * BT + h * 64);
-            mbar_wait(&q_full[st], (i / Q_STAGES) & 1);        // LSE / D_i staging visible
-            mbar_wait(s_full, i & 1);
+            mbar_wait(&q_full[st], (G / Q_STAGES) & 1);        // LSE / D_i staging visible
+            mbar_wait(s_full, G & 1);
             tc_fence_after();
             if (warp == 0) TL(8);
+            if (i == 0 && threadIdx.x == 0) TLC(1);
             uint32_t pk[32];                                    // P^T row (64 values) rounded to 16 bit
             {
                 uint32_t sr[2][32];
@@ -336,7 +379,7 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
             if (lane == 0) mbar_arrive(p_full);
             if (warp == 0) TL(9);
 
-            mbar_wait(dp_full, i & 1);
+            mbar_wait(dp_full, G & 1);
             tc_fence_after();
             if (warp == 0) TL(10);
             uint32_t dr[2][32];
@@ -344,7 +387,12 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
             tmem_ld32(tDP + 32, dr[1]);
             tmem_wait_ld();
             tc_fence_before();              // dP reads are complete before dQ may overwrite the columns
-            if (i > 0) mbar_wait(ds_empty, (i - 1) & 1);        // dK(i-1), dQ(i-1) finished reading dS smem
+            if (G > 0) mbar_wait(ds_empty, (G - 1) & 1);        // dK(G-1), dQ(G-1) finished reading dS smem
+            if (i == 0 && it > 0) {
+                // ... and so has the previous item's last dK / dV store, which was staged in this atom
+                if (issuer) tma_store_wait_read<0>();
+                named_bar_sync(ep_bar, 128);
+            }
             // dS^T = P^T o (dP^T - D_i): the difference in fp32, the product in packed 16-bit (it is rounded
             // to 16 bit for the tensor core anyway)
 #pragma unroll
@@ -378,31 +426,46 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
             if (warp == 0) TL(11);
         }
 
-        // epilogue: warpgroup 0 stores dK (scaled by 1/sqrt(D)), warpgroup 1 stores dV
-        mbar_wait(dkdv_full, 0);
+        // epilogue: warpgroup 0 stores dK (scaled by 1/sqrt(D)), warpgroup 1 stores dV, 32 columns at a time
+        // through this warpgroup's (now dead) dS atom as a 128B-swizzled fp32 box -> TMA store (rows past S are
+        // clipped by the tensor map).  The MMA warp is already computing S / dP of the next item.
+        mbar_wait(dkdv_full, it & 1);
         tc_fence_after();
-        const int row = kv_row0 + n;
-        const bool row_ok = row < p.S;
-        float* dst = (h == 0 ? p.dK : p.dV) + (static_cast<size_t>(bh) * p.S + (row_ok ? row : 0)) * p.D;
+        if (threadIdx.x == 0) TLC(2);
         const float mul = (h == 0) ? p.scale : 1.0f;
         const uint32_t tsrc = tmem_base + lane_addr + (h == 0 ? COL_DK : COL_DV);
+        const CUtensorMap* tm_out = (h == 0) ? &p.tm_dk : &p.tm_dv;
 #pragma unroll
         for (int c = 0; c < DP / 32; ++c) {
-            uint32_t r[32];
-            tmem_ld32(tsrc + c * 32, r);
-            tmem_wait_ld();
-            if (row_ok && c * 32 < p.D) {
+            if (c < n_chunk) {
+                uint32_t r[32];
+                tmem_ld32(tsrc + c * 32, r);
+                tmem_wait_ld();
+                if (c > 0) {
+                    if (issuer) tma_store_wait_read<0>();       // the previous chunk has left the staging atom
+                    named_bar_sync(ep_bar, 128);
+                }
 #pragma unroll
-                for (int i = 0; i < 32; i += 4) {
+                for (int q4 = 0; q4 < 8; ++q4) {
                     float4 v4;
-                    v4.x = __uint_as_float(r[i]) * mul;
-                    v4.y = __uint_as_float(r[i + 1]) * mul;
-                    v4.z = __uint_as_float(r[i + 2]) * mul;
-                    v4.w = __uint_as_float(r[i + 3]) * mul;
-                    *reinterpret_cast<float4*>(dst + c * 32 + i) = v4;
+                    v4.x = __uint_as_float(r[q4 * 4]) * mul;
+                    v4.y = __uint_as_float(r[q4 * 4 + 1]) * mul;
+                    v4.z = __uint_as_float(r[q4 * 4 + 2]) * mul;
+                    v4.w = __uint_as_float(r[q4 * 4 + 3]) * mul;
+                    *reinterpret_cast<float4*>(ds_atom + swz128(n, q4)) = v4;
+                }
+                fence_proxy_async_smem();
+                named_bar_sync(ep_bar + 1, 128);
+                if (issuer) {
+                    tma_store_3d(tm_out, ds_atom, c * 32, kv_row0, bh);
+                    tma_store_commit();
                 }
             }
         }
+        tc_fence_before();                  // dK / dV reads are complete before the next item's MMAs overwrite them
+        if (threadIdx.x == 0) TLC(3);
+        }
+        if (issuer) tma_store_wait<0>();    // global writes done before the CTA retires
     } else if (warp < MMA_WARP) {
         // ------------------------------------------------------------------ dQ drain warps
         setmaxnreg_dec<88>();
@@ -416,6 +479,10 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
         const int n_chunk = (p.D + 31) / 32;                   // real columns only (D = 32 under DP = 64)
         const uint32_t bar_id = 1 + 2 * h;                      // named barriers private to this warpgroup
 
+        int it = 0;
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+        const int bh = w / n_tiles, kv_tile = w % n_tiles;
+        auto q_row_of = [&](int i) { return q_row_at(kv_tile, i); };
         auto put_chunk = [&](const uint32_t (&rc)[32], int chunk, int i) {
             if (issuer) tma_store_wait_read<0>();               // previous reduce out of the buffer has been read
             named_bar_sync(bar_id, 128);
@@ -437,7 +504,7 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
         };
 
         for (int i = 0; i < n_tiles; ++i) {
-            mbar_wait(dq_full, i & 1);
+            mbar_wait(dq_full, (it * n_tiles + i) & 1);
             tc_fence_after();
             if (warp == D_WARP0) TL(15);
             uint32_t r[CPW][32];
@@ -458,6 +525,7 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
             }
             if (warp == D_WARP0) TL(17);
         }
+        }
         if (issuer) tma_store_wait<0>();
     } else {
         setmaxnreg_dec<40>();              // warps 18, 19: register donors only
@@ -476,7 +544,17 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
 cudaError_t launch_bwd(const BwdParams& p, cudaStream_t st) {
     const int DP = padded_head_dim(p.D);
     const int n_tiles = (p.S + BT - 1) / BT;
-    const dim3 grid(static_cast<unsigned>(p.BH) * n_tiles);
+    // persistent: one CTA per SM (or fewer when there is less work), each walks its share of the work items
+    static int sm_count[64] = {0};
+    int dev = 0;
+    cudaError_t e0 = cudaGetDevice(&dev);
+    if (e0 != cudaSuccess) return e0;
+    if (dev < 64 && sm_count[dev] == 0 &&
+        (e0 = cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess)
+        return e0;
+    const long long n_work = static_cast<long long>(p.BH) * n_tiles;
+    const int n_sm = dev < 64 ? sm_count[dev] : 148;
+    const dim3 grid(static_cast<unsigned>(n_work < n_sm ? n_work : n_sm));
     cudaError_t e;
     auto go = [&](auto kern, int smem) -> cudaError_t {
         cudaError_t err = ensure_smem_optin(reinterpret_cast<const void*>(kern), smem);

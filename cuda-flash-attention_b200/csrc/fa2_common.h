@@ -34,6 +34,8 @@ struct BwdParams {
     CUtensorMap tm_v;
     CUtensorMap tm_do;
     CUtensorMap tm_dq;   // fp32 [BH][S][D], box {32, 128, 1}, 128B swizzle (reduce-add target)
+    CUtensorMap tm_dk;   // same geometry, plain store targets
+    CUtensorMap tm_dv;
     const float* lse_log2;  // fp32 [BH][S]  LSE * log2(e)
     const float* delta;     // fp32 [BH][S]  rowsum(dO * O)
     float* dQ;              // fp32 [BH][S][D], zeroed by the pre-pass, reduce-added here
