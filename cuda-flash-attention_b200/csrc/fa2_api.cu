@@ -9,6 +9,7 @@
 #include "fa2_common.h"
 
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <initializer_list>
@@ -214,7 +215,17 @@ int run_cast(const Prepared& pr, const float* Q, const float* K, const float* V,
     return FA2_OK;
 }
 
-int run_fwd_main(const Prepared& pr, float* O, float* LSE, cudaStream_t st) {
+// Tuning knob FA2_FUSE (default 3): bit 0 = the forward's donor warps cast dO and zero-fill dQ, bit 1 = the forward's
+// epilogue forms D_i and LSE*log2(e); whatever is switched off is done by the stand-alone backward pre-pass instead.
+int fuse_mask() {
+    static const int mask = [] { const char* ev = getenv("FA2_FUSE"); return ev ? (atoi(ev) & 3) : 3; }();
+    return mask;
+}
+
+// dO / dQ non-null = fused forward+backward: the forward kernel also writes the 16-bit dO copy, D_i, LSE*log2(e)
+// and zero-fills dQ, so no separate backward pre-pass is launched.
+int run_fwd_main(const Prepared& pr, float* O, float* LSE, cudaStream_t st, const float* dO = nullptr,
+                 float* dQ = nullptr) {
     FwdParams p{};
     int rc;
     if ((rc = make_tmap_16(&p.tm_q, pr.work + pr.wl.off_q, pr.BH, pr.S, pr.DP, 128, pr.bf16))) return rc;
@@ -224,6 +235,15 @@ int run_fwd_main(const Prepared& pr, float* O, float* LSE, cudaStream_t st) {
     p.O = O; p.LSE = LSE; p.BH = pr.BH; p.S = pr.S; p.D = pr.D;
     p.scale = pr.scale; p.scale_log2 = pr.scale_log2; p.bf16 = pr.bf16;
     p.timeline = g_timeline;
+    if (dO && dQ) {
+        const int mask = fuse_mask();
+        p.dO = dO;
+        if (mask & 1) { p.dOh = pr.work + pr.wl.off_do; p.dQ_zero = dQ; }
+        if (mask & 2) {
+        p.delta = reinterpret_cast<float*>(pr.work + pr.wl.off_delta);
+        p.lse_log2 = reinterpret_cast<float*>(pr.work + pr.wl.off_lse2);
+        }
+    }
     ProfScope prof(1, st);
     FA2_CUDA(launch_fwd(p, st));
     return FA2_OK;
@@ -620,11 +640,16 @@ int fa2_forward_backward(const float* Q, const float* K, const float* V, const f
     int rc = prepare(&pr, B, H, S, D, precision, true);
     if (rc) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-    // (Forking the dO cast / dQ zero-fill onto a side stream beside the forward was measured: no gain, the
-    // forward and the Q/K/V cast slow down by the same amount.)
+    // The backward's pre-pass is folded into the forward kernel here: its register-donor warps cast dO and
+    // zero-fill dQ in the shadow of the tensor-core loop, its epilogue forms D_i and LSE*log2(e).
     if ((rc = run_cast(pr, Q, K, V, st))) return rc;           // one 16-bit copy serves both passes
-    if ((rc = run_fwd_main(pr, O, LSE, st))) return rc;
-    if ((rc = run_bwd_prepass(pr, O, dO, LSE, dQ, 3, st))) return rc;
+    {
+        const int mask = fuse_mask();
+        if (mask == 0) {
+            if ((rc = run_fwd_main(pr, O, LSE, st))) return rc;
+        } else if ((rc = run_fwd_main(pr, O, LSE, st, dO, dQ))) return rc; // also prepares dO(16 bit), D_i, LSE*log2e, dQ = 0
+        if (mask != 3 && (rc = run_bwd_prepass(pr, O, dO, LSE, dQ, 3 & ~mask, st))) return rc;
+    }
     return run_bwd_main(pr, dQ, dK, dV, st);
 }
 

@@ -25,6 +25,12 @@ struct FwdParams {
     float scale_log2;   // log2(e) / sqrt(D)
     float scale;        // 1 / sqrt(D)
     int bf16;
+    // fused forward+backward only (all null otherwise): the forward also prepares the backward's side inputs
+    const float* dO;    // fp32 [BH][S][D]
+    void* dOh;          // 16-bit [BH][S][DP] copy of dO        (register-donor warps)
+    float* dQ_zero;     // fp32 [BH][S][D], zero-filled          (register-donor warps)
+    float* delta;       // fp32 [BH][S]  rowsum(dO * O)          (epilogue)
+    float* lse_log2;    // fp32 [BH][S]  LSE * log2(e)           (epilogue)
     unsigned long long* timeline;   // debug builds (-DFA2_TIMELINE) only
 };
 

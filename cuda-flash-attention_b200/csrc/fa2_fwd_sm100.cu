@@ -60,7 +60,7 @@ struct FwdSmem {
     static constexpr int ALLOC = BYTES + 1024;                // slack for manual 1024-B alignment
 };
 
-template <int DP, bool BF16>
+template <int DP, bool BF16, bool FUSED>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 fa2_fwd_kernel(const __grid_constant__ FwdParams p) {
     using L = FwdSmem<DP>;
@@ -258,7 +258,47 @@ fa2_fwd_kernel(const __grid_constant__ FwdParams p) {
             }
         }
     } else if (warp >= 8) {
-        setmaxnreg_dec<56>();          // warps 10, 11: register donors only
+        // warps 10, 11: register donors.  In the fused forward+backward call they also do the backward's
+        // HBM-bound preparation in the shadow of the tensor-core loop: dO -> 16 bit (zero padded to DP) and the
+        // dQ zero-fill (the reference's cudaMemset before its backward launch, f-attn2-backward.cu:427).
+        setmaxnreg_dec<56>();
+        if (FUSED && p.dOh != nullptr) {
+            constexpr int LPR = DP / 8, RPW = 32 / LPR, U = 2;     // lanes per row, rows per warp pass, passes in flight
+            const int sub = lane / LPR, l = lane % LPR, col = l * 8;
+            const size_t rows = static_cast<size_t>(p.BH) * p.S;
+            const size_t wid = static_cast<size_t>(blockIdx.x) * 2 + (warp - 10), nw = static_cast<size_t>(gridDim.x) * 2;
+            uint4* dOh = static_cast<uint4*>(p.dOh);
+            float4* dq = reinterpret_cast<float4*>(p.dQ_zero);
+            const bool col_ok = col < p.D;
+            for (size_t base = wid * (RPW * U); base < rows; base += nw * (RPW * U)) {
+                float4 a[U], b[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const size_t row = base + u * RPW + sub;
+                    if (row < rows && col_ok) {
+                        a[u] = __ldcs(reinterpret_cast<const float4*>(p.dO + row * p.D + col));
+                        b[u] = __ldcs(reinterpret_cast<const float4*>(p.dO + row * p.D + col + 4));
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const size_t row = base + u * RPW + sub;
+                    if (row < rows) {
+                        uint4 out = make_uint4(0u, 0u, 0u, 0u);
+                        if (col_ok) {
+                            out.x = BF16 ? pack_bf16x2(a[u].x, a[u].y) : pack_half2(a[u].x, a[u].y);
+                            out.y = BF16 ? pack_bf16x2(a[u].z, a[u].w) : pack_half2(a[u].z, a[u].w);
+                            out.z = BF16 ? pack_bf16x2(b[u].x, b[u].y) : pack_half2(b[u].x, b[u].y);
+                            out.w = BF16 ? pack_bf16x2(b[u].z, b[u].w) : pack_half2(b[u].z, b[u].w);
+                            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                            __stcs(dq + ((row * p.D + col) >> 2), z);
+                            __stcs(dq + ((row * p.D + col) >> 2) + 1, z);
+                        }
+                        __stcs(dOh + row * LPR + l, out);
+                    }
+                }
+            }
+        }
     } else {
         // ------------------------------------------------------------------ softmax + epilogue
         setmaxnreg_inc<224>();
@@ -377,6 +417,19 @@ fa2_fwd_kernel(const __grid_constant__ FwdParams p) {
 
             // epilogue: O / l -> 128B-swizzled fp32 staging tile -> TMA store (rows past S are clipped by the
             // tensor map); LSE = ln(l) + m / sqrt(D).  The MMA warp is already computing S(0) of the next item.
+            // fused forward+backward: this thread also forms D_i = rowsum(dO o O) for its row (the reference's
+            // D_computation_reduction_kernel, f-attn2-backward.cu:342-380) while O is in registers; the dO row is
+            // fetched before the wait for the last P V so that its latency hides there.
+            const bool row_ok = q_row < p.S;
+            // (rows past S read row 0 of the slab: a valid address whose result is never stored)
+            const float4* do_row = reinterpret_cast<const float4*>(
+                (FUSED ? p.dO : p.O) + (static_cast<size_t>(bh) * p.S + (row_ok ? q_row : 0)) * p.D);
+            float4 dov[8];                                              // dO columns of the chunk being reduced
+            if constexpr (FUSED) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) dov[i] = __ldcs(do_row + i);
+            }
+            float dsum = 0.0f;
             mbar_wait(&o_full[t], mine & 1);
             tc_fence_after();
             if (threadIdx.x == 0) TLC(2);
@@ -387,6 +440,23 @@ fa2_fwd_kernel(const __grid_constant__ FwdParams p) {
                     uint32_t orr[32];
                     tmem_ld32(t_o + c * 32, orr);
                     tmem_wait_ld();
+                    if constexpr (FUSED) {
+#pragma unroll
+                        for (int q4 = 0; q4 < 8; ++q4) {
+                            const float4 d4 = dov[q4];
+                            dsum = fmaf(__uint_as_float(orr[q4 * 4]), d4.x, dsum);
+                            dsum = fmaf(__uint_as_float(orr[q4 * 4 + 1]), d4.y, dsum);
+                            dsum = fmaf(__uint_as_float(orr[q4 * 4 + 2]), d4.z, dsum);
+                            dsum = fmaf(__uint_as_float(orr[q4 * 4 + 3]), d4.w, dsum);
+                        }
+                        if (c + 1 < DP / 32) {
+                            // next chunk's dO, in flight during the store wait (unconditional loads keep dov in
+                            // registers; past the last real chunk the last one is simply fetched again)
+                            const int nc = (c + 1 < n_chunk) ? c + 1 : n_chunk - 1;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) dov[i] = __ldcs(do_row + nc * 8 + i);
+                        }
+                    }
                     if (issuer) tma_store_wait_read<0>();       // the previous store out of the buffer has been read
                     named_bar_sync(bar_id, 128);
 #pragma unroll
@@ -407,7 +477,15 @@ fa2_fwd_kernel(const __grid_constant__ FwdParams p) {
                     if (threadIdx.x == 0 && c < 3) TLC(5 + c);
                 }
             }
-            if (q_row < p.S) p.LSE[static_cast<size_t>(bh) * p.S + q_row] = m_ref * p.scale + logf(l_run);
+            if (row_ok) {
+                const size_t g = static_cast<size_t>(bh) * p.S + q_row;
+                const float lse = m_ref * p.scale + logf(l_run);
+                p.LSE[g] = lse;
+                if (FUSED && p.delta != nullptr) {
+                    p.delta[g] = dsum * inv_l;
+                    p.lse_log2[g] = lse * 1.4426950408889634f;      // same rounding as the stand-alone pre-pass
+                }
+            }
             if (threadIdx.x == 0) TLC(3);
             ++mine;
         }
@@ -445,8 +523,13 @@ cudaError_t launch_fwd(const FwdParams& p, cudaStream_t st) {
         kern<<<grid, NUM_THREADS, smem, st>>>(p);
         return cudaSuccess;
     };
-    if (DP == 64) e = p.bf16 ? go(fa2_fwd_kernel<64, true>, FwdSmem<64>::ALLOC) : go(fa2_fwd_kernel<64, false>, FwdSmem<64>::ALLOC);
-    else          e = p.bf16 ? go(fa2_fwd_kernel<128, true>, FwdSmem<128>::ALLOC) : go(fa2_fwd_kernel<128, false>, FwdSmem<128>::ALLOC);
+    const bool fused = p.dO != nullptr;
+#define FA2_FWD_GO(DPV) (p.bf16 ? (fused ? go(fa2_fwd_kernel<DPV, true, true>, FwdSmem<DPV>::ALLOC)    \
+                                         : go(fa2_fwd_kernel<DPV, true, false>, FwdSmem<DPV>::ALLOC))  \
+                                : (fused ? go(fa2_fwd_kernel<DPV, false, true>, FwdSmem<DPV>::ALLOC)   \
+                                         : go(fa2_fwd_kernel<DPV, false, false>, FwdSmem<DPV>::ALLOC)))
+    e = (DP == 64) ? FA2_FWD_GO(64) : FA2_FWD_GO(128);
+#undef FA2_FWD_GO
     if (e != cudaSuccess) return e;
     return cudaGetLastError();
 }
@@ -457,10 +540,14 @@ cudaError_t launch_fwd(const FwdParams& p, cudaStream_t st) {
 cudaError_t warm_fwd() {
     cudaFuncAttributes a;
     cudaError_t e;
-    if ((e = cudaFuncGetAttributes(&a, fa2_fwd_kernel<64, false>)) != cudaSuccess) return e;
-    if ((e = cudaFuncGetAttributes(&a, fa2_fwd_kernel<128, false>)) != cudaSuccess) return e;
-    if ((e = cudaFuncGetAttributes(&a, fa2_fwd_kernel<64, true>)) != cudaSuccess) return e;
-    return cudaFuncGetAttributes(&a, fa2_fwd_kernel<128, true>);
+    const void* kernels[] = {
+        reinterpret_cast<const void*>(fa2_fwd_kernel<64, false, false>), reinterpret_cast<const void*>(fa2_fwd_kernel<64, false, true>),
+        reinterpret_cast<const void*>(fa2_fwd_kernel<64, true, false>), reinterpret_cast<const void*>(fa2_fwd_kernel<64, true, true>),
+        reinterpret_cast<const void*>(fa2_fwd_kernel<128, false, false>), reinterpret_cast<const void*>(fa2_fwd_kernel<128, false, true>),
+        reinterpret_cast<const void*>(fa2_fwd_kernel<128, true, false>), reinterpret_cast<const void*>(fa2_fwd_kernel<128, true, true>)};
+    for (const void* k : kernels)
+        if ((e = cudaFuncGetAttributes(&a, k)) != cudaSuccess) return e;
+    return cudaSuccess;
 }
 
 }  // namespace fa2

@@ -113,7 +113,9 @@ def test_host_api_backward_default_dO_is_ones(U):
     for got, want in zip((O, L, dQ, dK, dV), t):
         assert U.maxerr(got, want) < 1e-2
     (dQ2, dK2, dV2), _ = fa2_b200.run_flash_attention(Q, K, V, O, L, mode="backward")
-    assert U.maxerr(dK2, dK) < 1e-5 and U.maxerr(dV2, dV) < 1e-5 and U.maxerr(dQ2, dQ) < 1e-4
+    # the fused call forms D_i = rowsum(dO o O) from the unnormalised accumulator inside the forward epilogue, the
+    # stand-alone backward from the stored fp32 O: an ulp of difference in D_i can flip a 16-bit rounding of dS
+    assert U.maxerr(dK2, dK) < 2e-4 and U.maxerr(dV2, dV) < 1e-5 and U.maxerr(dQ2, dQ) < 2e-4
 
 
 def test_host_api_chunked_pipeline_matches_device_api(U):
