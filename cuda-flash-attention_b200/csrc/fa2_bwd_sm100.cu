@@ -1,9 +1,11 @@
 // fa2_bwd_sm100.cu -- FlashAttention-2 backward for sm_100a (replaces the reference's
 // flash_attention2_backward_kernel, kernels/f-attn2-backward.cu:33-339).
 //
-// Like the reference, one CTA owns one KV tile of a (batch, head) slab and walks the Q tiles,
-// keeping dK / dV on chip and adding its dQ contribution into global memory
-// (reference: atomicAdd, f-attn2-backward.cu:298; here: TMA reduce-add in L2).  Tiles are
+// Like the reference, one work item is one KV tile of a (batch, head) slab: the CTA walks the Q
+// tiles, keeps dK / dV on chip and adds its dQ contribution into global memory (reference:
+// atomicAdd, f-attn2-backward.cu:298; here: TMA reduce-add in L2).  The kernel is persistent (one
+// CTA per SM, items taken round-robin, all mbarrier parities from running counters): the next
+// item's K/V load and S / dP MMAs overlap the dK / dV epilogue of the current one.  Tiles are
 // 128x128 and the five products run on the tensor cores, transposed so that the KV row is
 // the TMEM lane:
 //     S^T  = K Q^T          (SS, both K-major)            -> TMEM [384,512)
@@ -15,7 +17,8 @@
 //
 // Warp roles (20 warps = 5 warpgroups; within a pair of warpgroups, warpgroup h owns one half of the columns):
 //   0-3 / 4-7    compute:  S^T -> P^T = 2^(S^T c - lse2[q]) -> 16-bit into TMEM for the dV MMA, then
-//                          dS^T = P^T o (dP^T - D_i[q]) -> 128B-swizzled smem; at the end they store dK / dV
+//                          dS^T = P^T o (dP^T - D_i[q]) -> 128B-swizzled smem; at the end of an item they
+//                          store dK / dV (TMEM -> the dead dS atoms as fp32 staging boxes -> TMA store)
 //   8-11 / 12-15 dQ drain: TMEM -> registers (frees the dP/dQ columns at once) -> scaled, swizzled smem ->
 //                          cp.reduce.async.bulk.tensor add.  fp32 reduce-add sustains only ~24 B/clk per SM
 //                          (tools/reduce_probe.cu), i.e. >= 2730 cycles per 64 KB dQ tile -- more than the 2560

@@ -1,18 +1,23 @@
 // fa2_fwd_sm100.cu -- FlashAttention-2 forward for sm_100a (replaces the reference's
 // flash_attention2_forward_kernel, kernels/kernel_fa2_optimized.cu:19-347).
 //
-// One CTA owns 256 query rows of one (batch, head) slab as two 128-row tiles and walks the
-// 128-row KV tiles.  Roles (10 warps):
-//   warps 0-3  softmax for Q tile 0   (thread == one query row, TMEM lane == row)
-//   warps 4-7  softmax for Q tile 1
-//   warp  8    MMA issuer (one thread issues tcgen05.mma; the warp also owns TMEM alloc/free)
-//   warp  9    TMA producer (Q once, K/V double-buffered through shared memory)
+// Persistent kernel: one CTA per SM; work item = 256 query rows of one (batch, head) slab as two
+// 128-row tiles, walked over the 128-row KV tiles; items are taken round-robin so that the CTAs
+// running at the same time share the K/V of a few heads in L2.  Roles (12 warps):
+//   warps 0-3  softmax + epilogue for Q tile 0   (thread == one query row, TMEM lane == row)
+//   warps 4-7  softmax + epilogue for Q tile 1
+//   warp  8    MMA issuer (one elected thread issues tcgen05.mma; the warp also owns TMEM alloc/free)
+//   warp  9    TMA producer (Q per item, K/V double-buffered through shared memory)
+//   warps 10-11 register donors (setmaxnreg); in the fused forward+backward call they also cast dO to
+//              16 bit and zero-fill dQ for the backward while the tensor-core loop runs
 // S_t = Q_t K_j^T and O_t += P_t V_j run as tcgen05.mma (kind::f16, fp32 accumulate) with
 // S and O in TMEM; P is written back to TMEM over S as 16-bit and fed to the second MMA as
 // the A operand straight from TMEM.  The online softmax keeps max / sum per thread in
 // registers, works in the exp2 domain and only rescales O when the running max moved by
-// more than 2^8 (warp-uniform decision), then normalises and stores fp32 O and natural-log
-// LSE = ln(l) + m  (reference epilogue: kernel_fa2_optimized.cu:327-346).
+// more than 2^8 (warp-uniform decision).  Epilogue: O / l goes through a 128B-swizzled fp32
+// staging box and a TMA store, LSE = ln(l) + m (reference epilogue: kernel_fa2_optimized.cu:327-346);
+// meanwhile the MMA warp already computes S(0) of the next item.  Every mbarrier parity is derived
+// from running counters, so the pipeline never drains between items.
 #include "fa2_common.h"
 #include "ptx.cuh"
 
