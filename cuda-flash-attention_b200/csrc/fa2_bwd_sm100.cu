@@ -167,21 +167,28 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
             const int G = it * n_tiles + i;
             const int s = G % Q_STAGES;
             const uint32_t ph = (G / Q_STAGES) & 1;
+            // LSE (log2 domain) and D_i of this Q tile are fetched into registers BEFORE the wait for the stage, so
+            // that their global-memory latency is not on the Q(i) -> S(i) critical path; rows past S: +inf / 0
+            // => P = 0, dS = 0
+            float r_lse[BT / 32], r_dl[BT / 32];
+#pragma unroll
+            for (int r = 0; r < BT / 32; ++r) {
+                const int row = q_row_of(i) + r * 32 + lane;
+                const bool ok = row < p.S;
+                const size_t g = static_cast<size_t>(bh) * p.S + (ok ? row : 0);
+                r_lse[r] = ok ? __ldg(p.lse_log2 + g) : INFINITY;
+                r_dl[r] = ok ? __ldg(p.delta + g) : 0.0f;
+            }
             mbar_wait(&q_empty[s], ph ^ 1);
             if (elect_one()) {
                 mbar_expect_tx(&q_full[s], L::TILE);
                 for (int a = 0; a < DP / 64; ++a)
                     tma_load_3d(smem + L::OFF_Q + s * L::TILE + a * ATOM, &p.tm_q, &q_full[s], a * 64, q_row_of(i), bh);
             }
-            // stage LSE (log2 domain) and D_i of this Q tile; rows past S: +inf / 0  => P = 0, dS = 0
 #pragma unroll
             for (int r = 0; r < BT / 32; ++r) {
-                const int m = r * 32 + lane;
-                const int row = q_row_of(i) + m;
-                const bool ok = row < p.S;
-                const size_t g = static_cast<size_t>(bh) * p.S + (ok ? row : 0);
-                lse_s[s * BT + m] = ok ? __ldg(p.lse_log2 + g) : INFINITY;
-                delta_s[s * BT + m] = ok ? __ldg(p.delta + g) : 0.0f;
+                lse_s[s * BT + r * 32 + lane] = r_lse[r];
+                delta_s[s * BT + r * 32 + lane] = r_dl[r];
             }
             __syncwarp();
             if (elect_one()) mbar_arrive(&q_full[s]);           // LSE / D_i staged (the Q tile itself lands via TMA)

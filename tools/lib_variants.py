@@ -20,16 +20,23 @@ def run(lib, n):
     torch.cuda.synchronize()
 
 
+# The box is power-capped: after any idle gap the clocks boost and then sag, so whoever runs first in a round looks
+# faster.  Alternate the order every round, run long enough for the clocks to settle, and report the MEAN over rounds.
+import collections
+acc = collections.defaultdict(lambda: [0.0, 0.0, 0])
 for p, lib in libs:
     lib.fa2_profile_enable(1)
     run(lib, 2)
-for rnd in range(5):
-    for p, lib in libs:
+for rnd in range(6):
+    order = libs if rnd % 2 == 0 else libs[::-1]
+    for p, lib in order:
         ms = (ctypes.c_float * 4)(); n = (ctypes.c_int * 4)()
+        run(lib, 3)                      # settle
         lib.fa2_profile_read(ms, n)
         ms = (ctypes.c_float * 4)(); n = (ctypes.c_int * 4)()
-        run(lib, 4)
+        run(lib, 12)
         lib.fa2_profile_read(ms, n)
-        best[p][0] = min(best[p][0], ms[1] / n[1]); best[p][1] = min(best[p][1], ms[3] / n[3])
+        acc[p][0] += ms[1] / n[1]; acc[p][1] += ms[3] / n[3]; acc[p][2] += 1
 for p, _ in libs:
-    print(f"{p.split('/')[-1]:24s} fwd {best[p][0]:.3f} ms   bwd {best[p][1]:.3f} ms")
+    a = acc[p]
+    print(f"{p.split('/')[-1]:24s} fwd {a[0] / a[2]:.3f} ms   bwd {a[1] / a[2]:.3f} ms   (mean of {a[2]} rounds of 12 steps)")
