@@ -32,13 +32,18 @@ constexpr int NUM_THREADS = 384;        // 3 warpgroups; warps 10, 11 only donat
 constexpr int MMA_WARP = 8;
 constexpr int TMA_WARP = 9;
 constexpr float RESCALE_THRESHOLD = 8.0f;   // log2 units
-#ifndef FA2_POLY_EVERY
-#define FA2_POLY_EVERY 0
+// Which exponentials go through the FMA-pipe polynomial (ex2_poly2) instead of MUFU.EX2: one bit per group of 4
+// columns inside a 32-column chunk, FA2_POLY_A for the first pair of the group, FA2_POLY_B for the second.
+// MUFU (16 exps/clk/SM, shared by both softmax warpgroups) is a co-bottleneck of the forward; with the persistent
+// kernel a 25 % offload (B = 0x55) measures 6-8 % faster at D=64 and D=128 (tools/fwd_variants.py), 50 % is slower
+// again (FMA-pipe issue slots).
+#ifndef FA2_POLY_A
+#define FA2_POLY_A 0x00
 #endif
-// 0: all exps on MUFU; k: one pair in every k groups of 4 goes through the FMA-pipe polynomial (2 -> 25 %).
-// Measured on B200 at config C (tools/fwd_variants.py, round-robin best of 6): k=0 1.810 ms, k=4 1.843, k=2 1.910,
-// k=1 1.967 -- the softmax warps are issue/latency-bound, not MUFU-bound, so the offload is off by default.
-constexpr int POLY_EVERY = FA2_POLY_EVERY;
+#ifndef FA2_POLY_B
+#define FA2_POLY_B 0x55
+#endif
+constexpr unsigned POLY_A = FA2_POLY_A, POLY_B = FA2_POLY_B;
 
 #ifdef FA2_TIMELINE
 #define TLF(slot) do { if (p.timeline && w == 0 && lane == 0 && j < 32) p.timeline[j * 32 + (slot)] = clock64(); } while (0)
@@ -399,10 +404,8 @@ fa2_fwd_kernel(const __grid_constant__ FwdParams p) {
                     for (int i = 0; i < 32; i += 4) {
                         const float2 x0 = __ffma2_rn(make_float2(__uint_as_float(sr[c][i]), __uint_as_float(sr[c][i + 1])), c2v, nmv);
                         const float2 x1 = __ffma2_rn(make_float2(__uint_as_float(sr[c][i + 2]), __uint_as_float(sr[c][i + 3])), c2v, nmv);
-                        const float2 e0 = make_float2(ex2_approx(x0.x), ex2_approx(x0.y));
-                        // every POLY_EVERY-th group computes its second pair with the FMA-pipe polynomial (off)
-                        const float2 e1 = (POLY_EVERY > 0 && ((i >> 2) % (POLY_EVERY > 0 ? POLY_EVERY : 1)) == 0)
-                                              ? ex2_poly2(x1) : make_float2(ex2_approx(x1.x), ex2_approx(x1.y));
+                        const float2 e0 = ((POLY_A >> (i >> 2)) & 1u) ? ex2_poly2(x0) : make_float2(ex2_approx(x0.x), ex2_approx(x0.y));
+                        const float2 e1 = ((POLY_B >> (i >> 2)) & 1u) ? ex2_poly2(x1) : make_float2(ex2_approx(x1.x), ex2_approx(x1.y));
                         ls0 = __fadd2_rn(ls0, e0);
                         ls1 = __fadd2_rn(ls1, e1);
                         pk[i >> 1] = BF16 ? pack_bf16x2(e0.x, e0.y) : pack_half2(e0.x, e0.y);
