@@ -155,3 +155,52 @@ def test_backward_bf16_operands_and_fp16_flag(U):
     for prec, tol in (("bf16", 3e-2), ("fp16", U.TOL_GRAD)):
         dQ, dK, dV = U.gpu_backward(Q, K, V, tO.astype(np.float32), dO, tL.astype(np.float32), precision=prec)
         assert max(U.maxerr(dQ, tdQ), U.maxerr(dK, tdK), U.maxerr(dV, tdV)) < tol, prec
+
+
+def _fp64_truth_gpu(q, k, v, g):
+    """All heads at once in float64 on the GPU: O, LSE, dQ, dK, dV."""
+    import torch
+    D = q.shape[-1]
+    q, k, v, g = (t.double() for t in (q, k, v, g))
+    s = torch.einsum("bhqd,bhkd->bhqk", q, k) / (D ** 0.5)
+    lse = torch.logsumexp(s, -1)
+    p = torch.exp(s - lse[..., None])
+    o = p @ v
+    dv = p.transpose(-1, -2) @ g
+    dp = g @ v.transpose(-1, -2)
+    ds = p * (dp - (g * o).sum(-1, keepdim=True)) / (D ** 0.5)
+    return o, lse, ds @ k, ds.transpose(-1, -2) @ q, dv
+
+
+@pytest.mark.parametrize("shape", [(2, 40, 640, 64), (1, 100, 384, 128), (1, 160, 200, 32)],
+                         ids=lambda s: "B%d_H%d_S%d_D%d" % s)
+def test_persistent_schedule_several_items_per_cta(U, shape):
+    """More work items than SMs, so every persistent CTA walks several of them (barrier parities come from running
+    counters), and S chosen so that the last forward item of each head has only ONE query tile (the second
+    softmax warpgroup skips it) and the last KV / Q tile is ragged.  Checked against float64 for every head, for
+    the stand-alone calls and the fused call."""
+    import torch
+    import fa2_b200
+    gen = torch.Generator(device="cuda").manual_seed(31)
+    q, k, v, g = (torch.randn(*shape, device="cuda", generator=gen) for _ in range(4))
+    t = _fp64_truth_gpu(q, k, v, g)
+    o, l = fa2_b200.forward(q, k, v)
+    grads = fa2_b200.backward(q, k, v, o, g, l)
+    fused = fa2_b200.forward_backward(q, k, v, g)
+    torch.cuda.synchronize()
+    for got in ((o, l) + tuple(grads), fused):
+        for x, want, tol in zip(got, t, (U.TOL_O, U.TOL_LSE, U.TOL_GRAD, U.TOL_GRAD, U.TOL_GRAD)):
+            assert float((x.double() - want).abs().max()) < tol
+
+
+def test_long_sequence_config_D_slice(U):
+    """Two heads of config D (S = 16384, D = 128): 128 KV steps per forward item, 128 Q steps per backward item."""
+    import torch
+    import fa2_b200
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    q, k, v, g = (torch.randn(1, 2, 16384, 128, device="cuda", generator=gen) for _ in range(4))
+    got = fa2_b200.forward_backward(q, k, v, g)
+    torch.cuda.synchronize()
+    want = _fp64_truth_gpu(q[:, :1], k[:, :1], v[:, :1], g[:, :1])
+    for x, w, tol in zip(got, want, (U.TOL_O, U.TOL_LSE, U.TOL_GRAD, U.TOL_GRAD, U.TOL_GRAD)):
+        assert float((x[:, :1].double() - w).abs().max()) < tol
