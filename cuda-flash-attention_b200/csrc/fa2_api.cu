@@ -273,7 +273,7 @@ int run_bwd_main(const Prepared& pr, float* dQ, float* dK, float* dV, cudaStream
     if ((rc = make_tmap_f32(&p.tm_dv, dV, pr.BH, pr.S, pr.D))) return rc;
     p.lse_log2 = lse2; p.delta = delta; p.dQ = dQ; p.dK = dK; p.dV = dV;
     p.BH = pr.BH; p.S = pr.S; p.D = pr.D; p.scale = pr.scale; p.scale_log2 = pr.scale_log2; p.bf16 = pr.bf16;
-    p.timeline = g_timeline;
+    p.timeline = getenv("FA2_TL_FWD_ONLY") ? nullptr : g_timeline;     // (timeline builds: both kernels share the buffer)
     ProfScope prof(3, st);
     FA2_CUDA(launch_bwd(p, st));
     return FA2_OK;

@@ -430,12 +430,16 @@ fa2_fwd_kernel(const __grid_constant__ FwdParams p) {
             // fetched before the wait for the last P V so that its latency hides there.
             const bool row_ok = q_row < p.S;
             // (rows past S read row 0 of the slab: a valid address whose result is never stored)
-            const float4* do_row = reinterpret_cast<const float4*>(
-                (FUSED ? p.dO : p.O) + (static_cast<size_t>(bh) * p.S + (row_ok ? q_row : 0)) * p.D);
-            float4 dov[8];                                              // dO columns of the chunk being reduced
+            // Row-per-thread global loads cost the LSU one wavefront per lane per instruction whatever their width
+            // (measured: with 128-bit loads the four chunks added 5.7K cycles to every epilogue, with 256-bit loads
+            // 3.5K; tools/timeline_fwd.py ... fused), hence LDG.256.  Variants that read the staged O tile with
+            // coalesced dO loads, or request dO further ahead, either stall on the proxy fence before the TMA store
+            // (it waits for the thread's outstanding loads, ~2500 cycles each) or spill.
+            const float* do_row = (FUSED ? p.dO : p.O) + (static_cast<size_t>(bh) * p.S + (row_ok ? q_row : 0)) * p.D;
+            float dov[4][8];                                            // dO columns of the chunk being reduced
             if constexpr (FUSED) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) dov[i] = __ldcs(do_row + i);
+                for (int i = 0; i < 4; ++i) ldg256_stream(do_row + i * 8, dov[i]);
             }
             float dsum = 0.0f;
             mbar_wait(&o_full[t], mine & 1);
@@ -450,19 +454,13 @@ fa2_fwd_kernel(const __grid_constant__ FwdParams p) {
                     tmem_wait_ld();
                     if constexpr (FUSED) {
 #pragma unroll
-                        for (int q4 = 0; q4 < 8; ++q4) {
-                            const float4 d4 = dov[q4];
-                            dsum = fmaf(__uint_as_float(orr[q4 * 4]), d4.x, dsum);
-                            dsum = fmaf(__uint_as_float(orr[q4 * 4 + 1]), d4.y, dsum);
-                            dsum = fmaf(__uint_as_float(orr[q4 * 4 + 2]), d4.z, dsum);
-                            dsum = fmaf(__uint_as_float(orr[q4 * 4 + 3]), d4.w, dsum);
-                        }
+                        for (int i = 0; i < 32; ++i) dsum = fmaf(__uint_as_float(orr[i]), dov[i >> 3][i & 7], dsum);
                         if (c + 1 < DP / 32) {
                             // next chunk's dO, in flight during the store wait (unconditional loads keep dov in
                             // registers; past the last real chunk the last one is simply fetched again)
                             const int nc = (c + 1 < n_chunk) ? c + 1 : n_chunk - 1;
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) dov[i] = __ldcs(do_row + nc * 8 + i);
+                            for (int i = 0; i < 4; ++i) ldg256_stream(do_row + nc * 32 + i * 8, dov[i]);
                         }
                     }
                     if (issuer) tma_store_wait_read<0>();       // the previous store out of the buffer has been read

@@ -66,6 +66,14 @@ __device__ __forceinline__ float2 ex2_poly2(float2 x) {
     return r;
 }
 
+// 256-bit streaming global load (sm_100 LDG.256): 8 consecutive floats per lane.  For row-per-thread access patterns
+// the LSU cost is one wavefront per lane per instruction whatever the width, so wider loads halve it.
+__device__ __forceinline__ void ldg256_stream(const float* p, float (&a)[8]) {
+    asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a[0]), "=f"(a[1]), "=f"(a[2]), "=f"(a[3]), "=f"(a[4]), "=f"(a[5]), "=f"(a[6]), "=f"(a[7])
+                 : "l"(p));
+}
+
 __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
     uint32_t r;
     asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));

@@ -7,7 +7,7 @@ import sys
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-lib = ctypes.CDLL(os.path.join(ROOT, "cuda-flash-attention_b200", "build", "libfa2_b200_tl.so"))
+lib = ctypes.CDLL(os.environ.get("FA2_TL_LIB") or os.path.join(ROOT, "cuda-flash-attention_b200", "build", "libfa2_b200_tl.so"))
 B, H, S, D = (int(x) for x in (sys.argv[1:5] if len(sys.argv) >= 5 else (1, 8, 4096, 128)))
 q, k, v = (torch.randn(B, H, S, D, device="cuda") for _ in range(3))
 o = torch.empty_like(q); l = torch.empty(B, H, S, device="cuda")
@@ -17,7 +17,12 @@ P = lambda t: ctypes.c_void_p(t.data_ptr())
 for _ in range(2):
     lib.fa2_forward(P(q), P(k), P(v), P(o), P(l), B, H, S, D, 1, None)
 lib.fa2_debug_set_timeline(P(tl))
-lib.fa2_forward(P(q), P(k), P(v), P(o), P(l), B, H, S, D, 1, None)
+if len(sys.argv) > 5 and sys.argv[5] == "fused":      # the fused forward+backward variant of the forward kernel
+    os.environ["FA2_TL_FWD_ONLY"] = "1"
+    g = torch.randn_like(q); dq, dk, dv = (torch.empty_like(q) for _ in range(3))
+    lib.fa2_forward_backward(P(q), P(k), P(v), P(g), P(o), P(l), P(dq), P(dk), P(dv), B, H, S, D, 1, None)
+else:
+    lib.fa2_forward(P(q), P(k), P(v), P(o), P(l), B, H, S, D, 1, None)
 torch.cuda.synchronize()
 life = tl[1024:].cpu().view(n_cta, 8)
 t = tl[:1024].cpu().view(32, 32)
