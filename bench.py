@@ -66,17 +66,25 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Summarise the samples that arrived inside [t0, t1] (host clock around the timed region).  The sampler
+        is started before the warm-up steps (same workload), so a very short timed region that caught no sample
+        of its own falls back to the samples taken under the warm-up load and says so."""
         if self.proc:
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
             except Exception:
                 self.proc.kill()
+        window = "timed region"
+        rows = [r for t, r in self.rows if t0 is None or (t0 <= t <= t1 + 0.05)]
+        if not rows and self.rows:
+            rows = [r for t, r in self.rows if t >= t0 - 1.0] or [r for _, r in self.rows[-3:]]
+            window = "warm-up + timed region (timed region shorter than one sampling period)"
         sm, mx, reasons, pw = [], [], set(), []
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
@@ -87,7 +95,7 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw),
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def cpu_baseline(B, H, S, D, budget_s=12.0):
@@ -230,21 +238,23 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    sampler.start()               # before the warm-up: nvidia-smi takes a while to deliver its first sample
     for _ in range(args.warmup):
         step()
     barrier()
     lib.fa2_profile_enable(1)
-    sampler = ClockSampler(local)
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_host0 = time.perf_counter()
     e0.record(st)
     for _ in range(args.steps):
         step()
     e1.record(st)
     barrier()
+    t_host1 = time.perf_counter()
     ms_total = e0.elapsed_time(e1)
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_host0, t_host1)
     kms = (ctypes.c_float * 4)(0, 0, 0, 0)
     kn = (ctypes.c_int * 4)(0, 0, 0, 0)
     lib.fa2_profile_read(kms, kn)
