@@ -289,21 +289,72 @@ struct HostJob {
     int mode;   // FA2_MODE_*
 };
 
-// One device's share [bh0, bh0+count) of the slabs, processed in chunks through two device buffer sets and
+// One device's share [bh0, bh0+count) of the slabs, processed in chunks through kSets device buffer sets and
 // three streams so that the H2D copy of chunk c+1, the kernels of chunk c and the D2H copy of chunk c-1
 // overlap (PCIe is full duplex; the reference does malloc -> H2D -> kernel -> D2H -> free serially,
 // kernels/kernel_fa2_optimized.cu:371-421).
+// Streams and events of the host pipeline, kept per device between calls (creating ~60 of them costs ~0.7 ms per
+// call).  A second concurrent call on the same device finds the set busy and builds a private one.
+constexpr int kSets = 3;     // device buffer sets of the host pipeline (H2D of c+1, kernels of c, D2H of c-1 and its tail)
+struct PipeSet {
+    std::mutex mu;
+    bool ready = false;
+    cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[kSets] = {}, ev_comp[kSets] = {}, ev_out[kSets] = {};
+    std::vector<cudaEvent_t> k0, k1;          // timed events around each chunk's kernels
+
+    cudaError_t init() {
+        cudaError_t e;
+        if (!ready) {
+            if ((e = cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking)) != cudaSuccess) return e;
+            if ((e = cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking)) != cudaSuccess) return e;
+            if ((e = cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking)) != cudaSuccess) return e;
+            for (int i = 0; i < kSets; ++i) {
+                if ((e = cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming)) != cudaSuccess) return e;
+                if ((e = cudaEventCreateWithFlags(&ev_comp[i], cudaEventDisableTiming)) != cudaSuccess) return e;
+                if ((e = cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming)) != cudaSuccess) return e;
+            }
+            ready = true;
+        }
+        return cudaSuccess;
+    }
+    cudaError_t grow(size_t n) {
+        cudaError_t e;
+        while (k0.size() < n) {
+            cudaEvent_t a, b;
+            if ((e = cudaEventCreate(&a)) != cudaSuccess) return e;
+            if ((e = cudaEventCreate(&b)) != cudaSuccess) return e;
+            k0.push_back(a);
+            k1.push_back(b);
+        }
+        return cudaSuccess;
+    }
+    void destroy() {
+        if (!ready) return;
+        cudaStreamDestroy(s_in); cudaStreamDestroy(s_comp); cudaStreamDestroy(s_out);
+        for (int i = 0; i < kSets; ++i) { cudaEventDestroy(ev_in[i]); cudaEventDestroy(ev_comp[i]); cudaEventDestroy(ev_out[i]); }
+        for (cudaEvent_t e : k0) cudaEventDestroy(e);
+        for (cudaEvent_t e : k1) cudaEventDestroy(e);
+        k0.clear(); k1.clear();
+        ready = false;
+    }
+};
+PipeSet g_pipes[kMaxDevices];
+
 int host_worker(const HostJob& job, int dev, int bh0, int count, float* ms_out, std::string* err_out) {
     auto run = [&]() -> int {
         FA2_CUDA(cudaSetDevice(dev));
         const size_t slab = static_cast<size_t>(job.S) * job.D;           // floats per (b,h)
         const bool fwd = job.mode != FA2_MODE_BACKWARD, bwd = job.mode != FA2_MODE_FORWARD;
-        // chunk size: ~16 chunks per device, but never so small that a chunk cannot fill the SMs.  PCIe is full
+        // chunk size: ~32 chunks per device, but never so small that a chunk cannot fill the SMs.  PCIe is full
         // duplex (measured 2 x 47 GB/s against 55 GB/s one way), so the job takes (bytes one way) / 47 GB/s plus
-        // whatever time only one direction is busy: the H2D of the first chunk and the D2H of the last.  Those two
-        // are cut to a quarter with a short ramp (1/4, 1/2 of a chunk) at both ends.
+        // whatever time only one direction is busy: the H2D of the first chunk and, at the end, the D2H of
+        // everything still on the device when the last H2D finishes (about 1.25 chunks: the D2H of a chunk cannot
+        // start before its kernels, which cannot start before its H2D).  Hence small chunks (the kernels of a chunk
+        // take a fifth of its transfer time, so their efficiency does not matter here) and a short ramp
+        // (1/4, 1/2 of a chunk) at both ends.
         const int tiles = (job.S + 127) / 128;
-        int chunk_bh = (count + 15) / 16;
+        int chunk_bh = (count + 31) / 32;
         const int min_bh = (2 * 148 + tiles - 1) / tiles;
         if (chunk_bh < min_bh) chunk_bh = min_bh;
         if (chunk_bh > count) chunk_bh = count;
@@ -320,7 +371,7 @@ int host_worker(const HostJob& job, int dev, int bh0, int count, float* ms_out, 
         const size_t tb = align_up(slab * chunk_bh * 4, 1024), lb = align_up(static_cast<size_t>(job.S) * chunk_bh * 4, 1024);
         const size_t set_bytes = 4 * tb + lb + (bwd ? 4 * tb : 0);       // Q K V O LSE [dO dQ dK dV]
         void* base = nullptr;
-        int rc = arena_reserve(g_io, dev, 2 * set_bytes, &base);
+        int rc = arena_reserve(g_io, dev, kSets * set_bytes, &base);
         if (rc) return rc;
         {   // keep one-time costs (module load, workspace growth) out of the timed region
             Prepared warm;
@@ -328,21 +379,18 @@ int host_worker(const HostJob& job, int dev, int bh0, int count, float* ms_out, 
             FA2_CUDA(warm_fwd());
             FA2_CUDA(warm_bwd());
         }
-        cudaStream_t s_in, s_comp, s_out;
-        FA2_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
-        FA2_CUDA(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
-        FA2_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
-        cudaEvent_t ev_in[2], ev_comp[2], ev_out[2];
-        for (int i = 0; i < 2; ++i) {
-            FA2_CUDA(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
-            FA2_CUDA(cudaEventCreateWithFlags(&ev_comp[i], cudaEventDisableTiming));
-            FA2_CUDA(cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming));
-        }
-        std::vector<cudaEvent_t> k0(n_chunks), k1(n_chunks);
-        for (int c = 0; c < n_chunks; ++c) {
-            FA2_CUDA(cudaEventCreate(&k0[c]));
-            FA2_CUDA(cudaEventCreate(&k1[c]));
-        }
+        PipeSet local_set;                                  // only used when the device's cached set is busy
+        std::unique_lock<std::mutex> pipe_lock(g_pipes[dev].mu, std::try_to_lock);
+        PipeSet& ps = pipe_lock.owns_lock() ? g_pipes[dev] : local_set;
+        struct LocalGuard { PipeSet& s; bool on; ~LocalGuard() { if (on) s.destroy(); } } guard{local_set, !pipe_lock.owns_lock()};
+        FA2_CUDA(ps.init());
+        FA2_CUDA(ps.grow(static_cast<size_t>(n_chunks)));
+        cudaStream_t s_in = ps.s_in, s_comp = ps.s_comp, s_out = ps.s_out;
+        cudaEvent_t* ev_in = ps.ev_in;
+        cudaEvent_t* ev_comp = ps.ev_comp;
+        cudaEvent_t* ev_out = ps.ev_out;
+        std::vector<cudaEvent_t>& k0 = ps.k0;
+        std::vector<cudaEvent_t>& k1 = ps.k1;
         // FA2_HOST_TRACE=1: print when each chunk's copies and kernels ran (pipeline tuning aid)
         static const bool trace = getenv("FA2_HOST_TRACE") != nullptr;
         const auto wall0 = std::chrono::steady_clock::now();
@@ -354,7 +402,7 @@ int host_worker(const HostJob& job, int dev, int bh0, int count, float* ms_out, 
         }
         int cb0 = bh0;
         for (int c = 0; c < n_chunks; cb0 += sizes[c], ++c) {
-            const int set = c & 1;
+            const int set = c % kSets;
             const int cnt = sizes[c];
             const size_t n = slab * cnt, nl = static_cast<size_t>(job.S) * cnt;
             const size_t off = static_cast<size_t>(cb0) * slab, offl = static_cast<size_t>(cb0) * job.S;
@@ -368,8 +416,8 @@ int host_worker(const HostJob& job, int dev, int bh0, int count, float* ms_out, 
             float* dQ_ = bwd ? reinterpret_cast<float*>(b8 + 5 * tb + lb) : nullptr;
             float* dK_ = bwd ? reinterpret_cast<float*>(b8 + 6 * tb + lb) : nullptr;
             float* dV_ = bwd ? reinterpret_cast<float*>(b8 + 7 * tb + lb) : nullptr;
-            // inputs of this buffer set were consumed by the kernels of chunk c-2
-            if (c >= 2) FA2_CUDA(cudaStreamWaitEvent(s_in, ev_comp[set], 0));
+            // inputs of this buffer set were consumed by the kernels of chunk c-kSets
+            if (c >= kSets) FA2_CUDA(cudaStreamWaitEvent(s_in, ev_comp[set], 0));
             FA2_CUDA(cudaMemcpyAsync(dQin, job.Q + off, n * 4, cudaMemcpyHostToDevice, s_in));
             FA2_CUDA(cudaMemcpyAsync(dKin, job.K + off, n * 4, cudaMemcpyHostToDevice, s_in));
             FA2_CUDA(cudaMemcpyAsync(dVin, job.V + off, n * 4, cudaMemcpyHostToDevice, s_in));
@@ -380,9 +428,9 @@ int host_worker(const HostJob& job, int dev, int bh0, int count, float* ms_out, 
             if (bwd) FA2_CUDA(cudaMemcpyAsync(ddO, job.dO + off, n * 4, cudaMemcpyHostToDevice, s_in));
             FA2_CUDA(cudaEventRecord(ev_in[set], s_in));
             if (trace) FA2_CUDA(cudaEventRecord(tr[3 * c], s_in));
-            // kernels: need the inputs, and the outputs of chunk c-2 must have left this buffer set
+            // kernels: need the inputs, and the outputs of chunk c-kSets must have left this buffer set
             FA2_CUDA(cudaStreamWaitEvent(s_comp, ev_in[set], 0));
-            if (c >= 2) FA2_CUDA(cudaStreamWaitEvent(s_comp, ev_out[set], 0));
+            if (c >= kSets) FA2_CUDA(cudaStreamWaitEvent(s_comp, ev_out[set], 0));
             FA2_CUDA(cudaEventRecord(k0[c], s_comp));
             if (job.mode == FA2_MODE_FORWARD)
                 rc = fa2_forward(dQin, dKin, dVin, dO_, dL, 1, cnt, job.S, job.D, job.precision, s_comp);
@@ -435,18 +483,8 @@ int host_worker(const HostJob& job, int dev, int bh0, int count, float* ms_out, 
             float ms = 0.f;
             FA2_CUDA(cudaEventElapsedTime(&ms, k0[c], k1[c]));
             total_ms += ms;
-            cudaEventDestroy(k0[c]);
-            cudaEventDestroy(k1[c]);
         }
         *ms_out = total_ms;
-        for (int i = 0; i < 2; ++i) {
-            cudaEventDestroy(ev_in[i]);
-            cudaEventDestroy(ev_comp[i]);
-            cudaEventDestroy(ev_out[i]);
-        }
-        cudaStreamDestroy(s_in);
-        cudaStreamDestroy(s_comp);
-        cudaStreamDestroy(s_out);
         return FA2_OK;
     };
     int rc = run();
@@ -590,6 +628,14 @@ int fa2_release_workspaces(void) {
     int prev = 0;
     if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); return FA2_OK; }
     for (int d = 0; d < kMaxDevices; ++d) {
+        {
+            std::lock_guard<std::mutex> pl(g_pipes[d].mu);
+            if (g_pipes[d].ready) {
+                cudaSetDevice(d);
+                cudaDeviceSynchronize();
+                g_pipes[d].destroy();
+            }
+        }
         for (Arena* a : {&g_work[d], &g_io[d]}) {
             if (a->ptr) {
                 cudaSetDevice(d);

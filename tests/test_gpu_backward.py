@@ -119,7 +119,7 @@ def test_host_api_backward_default_dO_is_ones(U):
 
 
 def test_host_api_chunked_pipeline_matches_device_api(U):
-    """fa2_host_* streams the slabs through two buffer sets in chunks (H2D / kernels / D2H overlapped);
+    """fa2_host_* streams the slabs through three buffer sets in chunks (H2D / kernels / D2H overlapped);
     80 slabs of S=1024 make three chunks (37 + 37 + 6).  Results must equal the one-shot device path."""
     import torch
     import fa2_b200
