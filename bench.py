@@ -200,6 +200,11 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: the FA2 path has no CPU fallback")
     torch.cuda.set_device(local)
+    # rank 0 samples its GPU's clocks; started here, long before the timed region, because nvidia-smi needs a while
+    # to deliver its first sample (more so with eight ranks starting at once)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     dist = None
     if world > 1:
         # rank 0 must print exactly one JSON line on stdout, and NCCL prints its version banner there whenever
@@ -238,8 +243,6 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local)
-    sampler.start()               # before the warm-up: nvidia-smi takes a while to deliver its first sample
     for _ in range(args.warmup):
         step()
     barrier()
