@@ -63,7 +63,7 @@ struct BwdSmem {
     static constexpr int OFF_LSE = OFF_DQS + 2 * BT * 128;        // Q_STAGES x 128 fp32
     static constexpr int OFF_DELTA = OFF_LSE + Q_STAGES * BT * 4;
     static constexpr int OFF_BAR = OFF_DELTA + Q_STAGES * BT * 4;
-    static constexpr int NUM_BARS = 16;
+    static constexpr int NUM_BARS = 17;
     static constexpr int OFF_TMEM_PTR = OFF_BAR + NUM_BARS * 8;
     static constexpr int BYTES = OFF_TMEM_PTR + 16;
 };
@@ -93,6 +93,7 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
     uint64_t* dq_empty = bars + 13;
     uint64_t* dkdv_full = bars + 14;
     uint64_t* kv_empty = bars + 15;   // the item's last dQ / dP have read the K / V tiles
+    uint64_t* epi_issued = bars + 16; // both compute warpgroups have issued their last dK / dV store of the item
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + L::OFF_TMEM_PTR);
     float* lse_s = reinterpret_cast<float*>(smem + L::OFF_LSE);
     float* delta_s = reinterpret_cast<float*>(smem + L::OFF_DELTA);
@@ -137,6 +138,7 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
             mbar_init(dq_empty, 8);           // one arrive per drain warp
             mbar_init(dkdv_full, 1);
             mbar_init(kv_empty, 1);
+            mbar_init(epi_issued, 2);
             fence_mbar_init();
         }
         __syncwarp();
@@ -472,6 +474,7 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
                 }
             }
         }
+        if (issuer) mbar_arrive(epi_issued);
         tc_fence_before();                  // dK / dV reads are complete before the next item's MMAs overwrite them
         if (threadIdx.x == 0) TLC(3);
         }
@@ -526,6 +529,10 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
             if (lane == 0) mbar_arrive(dq_empty);               // dP(i+1) may overwrite the columns now
             if (warp == D_WARP0) TL(16);
 
+            // The SM's write path (~24 B/clk) is shared with the compute warps' dK / dV stores at the end of an item,
+            // and those gate the next item: the last tile's reduce (which gates nothing; these warps are idle for
+            // the first ~5K cycles of the next item anyway) waits until they have all been issued.
+            if (i == n_tiles - 1) mbar_wait(epi_issued, it & 1);
             // Only the drain warps ever wait for the reduce engine (they hold the tile in registers).
 #pragma unroll
             for (int c = 0; c < CPW; ++c) {

@@ -8,7 +8,7 @@ import sys
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-lib = ctypes.CDLL(os.path.join(ROOT, "cuda-flash-attention_b200", "build", "libfa2_b200_tl.so"))
+lib = ctypes.CDLL(os.environ.get("FA2_TL_LIB") or os.path.join(ROOT, "cuda-flash-attention_b200", "build", "libfa2_b200_tl.so"))
 B, H, S, D = (int(x) for x in (sys.argv[1:5] if len(sys.argv) >= 5 else (1, 8, 4096, 128)))
 q, k, v, g = (torch.randn(B, H, S, D, device="cuda") for _ in range(4))
 o = torch.empty_like(q); l = torch.empty(B, H, S, device="cuda")
