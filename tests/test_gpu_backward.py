@@ -217,3 +217,18 @@ def test_fused_forward_backward_bf16_operands(U):
     torch.cuda.synchronize()
     for x, w, tol in zip(got, want, (1e-2, 5e-3, 3e-2, 3e-2, 3e-2)):     # bf16: 8-bit mantissa (SURVEY finding F5)
         assert float((x.double() - w).abs().max()) < tol
+
+
+def test_release_workspaces_then_reuse(U):
+    """fa2_release_workspaces() frees the per-device arenas and the cached pipeline streams / events; the next calls
+    (device API and host API) must rebuild them and give the same results."""
+    import fa2_b200
+    Q, K, V, dO = U.randn_case((1, 4, 300, 64), seed=12)
+    (O1, L1, dQ1, dK1, dV1), _ = fa2_b200.run_flash_attention(Q, K, V, dO=dO, mode="forward_backward")
+    fa2_b200._lib.check(fa2_b200._lib.load().fa2_release_workspaces())
+    (O2, L2, dQ2, dK2, dV2), _ = fa2_b200.run_flash_attention(Q, K, V, dO=dO, mode="forward_backward")
+    assert np.array_equal(O1, O2) and np.array_equal(L1, L2) and np.array_equal(dK1, dK2) and np.array_equal(dV1, dV2)
+    assert U.maxerr(dQ1, dQ2) < 1e-5
+    fa2_b200._lib.check(fa2_b200._lib.load().fa2_release_workspaces())
+    O3, L3 = U.gpu_forward(Q, K, V)
+    assert np.array_equal(O1, O3) and np.array_equal(L1, L3)
