@@ -232,3 +232,20 @@ def test_release_workspaces_then_reuse(U):
     fa2_b200._lib.check(fa2_b200._lib.load().fa2_release_workspaces())
     O3, L3 = U.gpu_forward(Q, K, V)
     assert np.array_equal(O1, O3) and np.array_equal(L1, L3)
+
+
+def test_host_api_two_gpus_match_one_gpu(U):
+    """fa2_host_forward_backward with n_gpus = 2: each device takes a contiguous (b,h) slab range (fa2_partition), no
+    collective; results must equal the single-GPU run (dQ up to reduce order).  Needs a 2-GPU box."""
+    import torch
+    import fa2_b200
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    Q, K, V, dO = U.randn_case((3, 5, 640, 128), seed=41)          # 15 slabs: 7 + 8
+    one, _ = fa2_b200.run_flash_attention(Q, K, V, dO=dO, mode="forward_backward", n_gpus=1)
+    two, _ = fa2_b200.run_flash_attention(Q, K, V, dO=dO, mode="forward_backward", n_gpus=2)
+    for a, b, exact in zip(one, two, (True, True, False, True, True)):
+        if exact:
+            assert np.array_equal(a, b)
+        else:
+            assert U.maxerr(a, b) < 1e-5
