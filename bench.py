@@ -4,16 +4,20 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload C|A|B|D]
     (N > 1: python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...)
 
-A step = one forward + backward pass (4 kernels: fp32->fp16 cast, forward, backward pre-pass,
-backward) over one synthetic batch of the workload, on fp32 [B,H,S,D] device tensors.
-Default workload = BASELINE.json configs[2], B8 H32 S4096 D128 (the shape the metric is quoted
-on); with N ranks every rank runs that shape on its own slab range of a global batch 8*N
-(weak scaling, no data-path collective -- (batch, head) slabs are independent).
+A step = one forward + backward pass (cast, forward [+ fused backward pre-pass], backward) over one
+synthetic batch of the workload, on fp32 [B,H,S,D] device tensors.  Default workload = BASELINE.json
+configs[2], B8 H32 S4096 D128 (the shape the metric is quoted on); with N ranks every rank runs that
+shape on its own slab range of a global batch 8*N (weak scaling, no data-path collective -- (batch,
+head) slabs are independent).  After the timed loop the TIMED outputs are checked against a float64
+reference on sampled (b,h) slabs; a wrong answer makes the run exit non-zero.  At N > 1 rank 0 also
+runs ONE workload-sized problem through fa2_host_forward_backward(n_gpus=N) -- the north_star
+partitioner -- and reports its strong scaling against n_gpus=1.
 Rank 0 prints ONE JSON line.  FLOP convention: fwd 4*BHS^2*D, bwd 10*BHS^2*D.
 """
 import argparse
 import json
 import os
+import re
 import statistics
 import subprocess
 import sys
@@ -28,13 +32,24 @@ sys.path.insert(0, os.path.join(ROOT, "cuda-flash-attention_b200"))
 WORKLOADS = {   # BASELINE.json configs
     "A": (2, 8, 512, 64), "B": (4, 16, 1024, 64), "C": (8, 32, 4096, 128), "D": (1, 16, 16384, 128),
 }
+PRECISION_OF = {"A": "fp32", "B": "fp16", "C": "fp32", "D": "fp32"}      # configs[1] names the fp16 SHM flag
 METRIC = "FA2 fwd+bwd TFLOPS/GPU-aggregate, B8 H32 S4096 D128 per GPU"
 UNIT = "TFLOP/s"
+TOL = {"O": 1e-2, "LSE": 1e-3, "dQ": 1e-2, "dK": 1e-2, "dV": 1e-2}        # north_star, 16-bit operands
 
 
 def flops(B, H, S, D):
     f = 4.0 * B * H * S * S * D
     return f, 2.5 * f
+
+
+def compulsory_bytes(B, H, S, D):
+    n = B * H * S
+    return 16 * n * D + 4 * n, 32 * n * D + 4 * n          # fwd, bwd
+
+
+def workload_name(key, B, H, S, D):
+    return f"configs[{'ABCD'.index(key)}] B{B} H{H} S{S} D{D} fwd+bwd"
 
 
 def measured_peaks():
@@ -126,51 +141,89 @@ def cpu_baseline(B, H, S, D, budget_s=12.0):
 
 
 def run_reference(args):
-    """--impl reference: the UNMODIFIED reference CLI (oracle/_ref/FlashAttention_ref, its own sources
-    compiled for sm_100) run through its own argv surface; the number is its own TimerGPU total
-    ('Kernel execution completed', src/main.cpp:107).  The reference rejects D=128
-    (include/dispatcher.h:226-227), so each step is a bounded equal-S sample at D=64."""
+    """--impl reference: the reference's OWN fa2 fp32 kernels and host launchers (kernel_fa2_optimized.cu:351-423,
+    f-attn2-backward.cu:384-485), compiled from where they lie in /root/reference into oracle/_ref/ref_any_d
+    (oracle/build_ref.sh), run on the SAME workload as the b200 arm.  The reference's dispatcher refuses D=128
+    (include/dispatcher.h:226-227), so ref_any_d instantiates its templates at the workload's head dim; nothing else
+    is changed.  The reference has no CPU implementation of this path: its kernels run on the B200's CUDA cores.
+    `value` = its TimerGPU kernel time (src/main.cpp:107 semantics), `e2e` = wall clock of its host launchers
+    (pageable host buffers, cudaMalloc / H2D / D2H / cudaFree inside, as RunFlashAttention does)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    exe = os.path.join(ROOT, "oracle", "_ref", "FlashAttention_ref")
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_any_d")
+    key = args.workload
+    B, H, S, D = WORKLOADS[key]
     if not os.path.exists(exe):
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/FlashAttention_ref not built (run __graft_entry__.build() where /root/reference exists)"}))
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_any_d not built (run __graft_entry__.build() where /root/reference exists)"}))
         return
-    import numpy as np
-    B, H, S, D = 2, 16, 4096, 64            # 32 slabs x S4096: fills the GPU, 1/8 of config C's fwd FLOPs... at D=64
-    f, b = flops(B, H, S, D)
-    times = []
-    with tempfile.TemporaryDirectory() as tmp:
-        d = os.path.join(tmp, f"B{B}_H{H}_S{S}_D{D}")
-        os.makedirs(d)
-        rng = np.random.default_rng(42)
-        for n in "QKV":
-            rng.standard_normal((B, H, S, D), dtype=np.float32).tofile(os.path.join(d, f"{n}.bin"))
-        t_wall0 = time.perf_counter()
-        for i in range(args.warmup + args.steps):
-            out = subprocess.run([exe, "fa2", "forward_backward", "fp32", d], capture_output=True, text=True, timeout=600)
-            if out.returncode != 0:
-                print(json.dumps({"impl": "reference", "unavailable": "reference CLI failed: " + (out.stderr or out.stdout)[-200:].replace("\n", " ")}))
-                return
-            secs = [float(l.split(":")[1].split()[0]) for l in out.stdout.splitlines() if l.startswith("Kernel execution completed")]
-            if i >= args.warmup:
-                times.append(secs[0])
-        wall = time.perf_counter() - t_wall0
-    t = statistics.mean(times)
-    val = (f + b) / t / 1e12
+    budget = float(os.environ.get("FA2_REF_BUDGET_S", "150"))
+    try:
+        out = subprocess.run([exe, "--bench", str(B), str(H), str(S), str(D), str(args.steps), str(args.warmup), str(budget)],
+                             capture_output=True, text=True, timeout=1500)
+    except subprocess.TimeoutExpired:
+        print(json.dumps({"impl": "reference", "unavailable": "reference bench timed out"}))
+        return
+    m = re.search(r"^REF_BENCH (\{.*\})$", out.stdout, re.M)
+    if out.returncode != 0 or not m:
+        print(json.dumps({"impl": "reference", "unavailable": "reference bench failed: " + (out.stderr or out.stdout)[-300:].replace("\n", " ")}))
+        return
+    r = json.loads(m.group(1))
+    full = r["slabs_per_step"] == r["slabs_full"]
+    sample = (f"{r['steps']} timed steps of {r['slabs_per_step']} of {r['slabs_full']} (b,h) slabs of S{S} D{D} "
+              f"({'the full workload' if full else 'bounded slab subset, same S and D'}); reference fa2 fp32 kernels on the "
+              f"B200's CUDA cores via its own host launchers; total wall {r['total_wall_s']:.0f} s")
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": r["kernel_tflops"], "unit": UNIT, "n_gpus": 1, "steps": r["steps"],
+        "warmup": args.warmup, "ms_per_step": r["kernel_ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"B{B}_H{H}_S{S}_D{D} fa2 forward_backward fp32 through the reference CLI: bounded sample "
-                               "of the S4096 workload at D=64 because the reference rejects D=128 "
-                               "(include/dispatcher.h:226-227); device = B200 CUDA cores, kernels as shipped",
-                   "timer": "reference TimerGPU total (fwd kernel + D kernel + bwd kernel), src/main.cpp:107"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "reference",
-                         "sample": f"{args.steps} CLI runs of B{B}_H{H}_S{S}_D{D}; the reference has no CPU implementation, its fa2 kernels run on the GPU's CUDA cores; wall {wall:.1f} s incl. file I/O"},
-        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": {"workload": workload_name(key, B, H, S, D) + " per GPU",
+                   "reference_sample": sample,
+                   "timer": "reference TimerGPU total (fwd kernel + D kernel + bwd kernel), include/timer.h:50-64"},
+        "cpu_baseline": {"value": r["kernel_tflops"], "unit": UNIT, "cores": 1, "kind": "reference", "sample": sample},
+        "e2e": {"value": r["e2e_tflops"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                "ms_per_step": r["wall_ms_per_step"],
+                "note": "wall clock of host_flash_attention2_forward + _backward on pageable host buffers (their own "
+                        "cudaMalloc/H2D/D2H/cudaFree inside)"},
     }))
+
+
+def fp64_slab(q, k, v, g):
+    """float64 O, LSE, dQ, dK, dV of one (b,h) slab on the GPU (checker only)."""
+    import torch
+    D = q.shape[-1]
+    q, k, v, g = (t.double() for t in (q, k, v, g))
+    s = (q @ k.T) / (D ** 0.5)
+    lse = torch.logsumexp(s, -1)
+    p = torch.exp(s - lse[:, None])
+    del s
+    o = p @ v
+    dv = p.T @ g
+    dp = g @ v.T
+    ds = p * (dp - (g * o).sum(-1, keepdim=True)) / (D ** 0.5)
+    del p, dp
+    return o, lse, ds @ k, ds.T @ q, dv
+
+
+def verify_outputs(q, k, v, g, outs, n_each=3):
+    """max-abs error of the given outputs against float64 on (b,h) slabs at the first, middle and last work items."""
+    import torch
+    B, H = q.shape[:2]
+    BH = B * H
+    picks = sorted(set(x for x in (list(range(n_each)) + list(range(BH // 2 - 1, BH // 2 - 1 + n_each)) +
+                                   list(range(BH - n_each, BH))) if 0 <= x < BH))
+    names = ("O", "LSE", "dQ", "dK", "dV")
+    err = {n: 0.0 for n in names}
+    finite = True
+    for bh in picks:
+        b, h = divmod(bh, H)
+        want = fp64_slab(q[b, h], k[b, h], v[b, h], g[b, h])
+        for n, got, w in zip(names, outs, want):
+            x = got[b, h]
+            finite = finite and bool(torch.isfinite(x).all())
+            err[n] = max(err[n], float((x.double() - w).abs().max()))
+        del want
+    return picks, err, finite
 
 
 def main():
@@ -182,6 +235,8 @@ def main():
     ap.add_argument("--workload", default="C", choices=sorted(WORKLOADS))
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-verify", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling leg at N > 1")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -206,6 +261,7 @@ def main():
     if rank == 0:
         sampler.start()
     dist = None
+    host_group = None
     if world > 1:
         # rank 0 must print exactly one JSON line on stdout, and NCCL prints its version banner there whenever
         # NCCL_DEBUG is set (the GPU image sets it): create the communicator with fd 1 pointed at stderr.
@@ -217,6 +273,8 @@ def main():
             dist.init_process_group("nccl", device_id=torch.device("cuda", local))
             dist.barrier()
             torch.cuda.synchronize()
+            # host-side barrier (gloo): ranks parked on it leave their GPU idle, unlike an NCCL barrier kernel
+            host_group = dist.new_group(backend="gloo")
         finally:
             sys.stdout.flush()
             os.dup2(saved, 1)
@@ -224,7 +282,9 @@ def main():
     if args.gpus != world and rank == 0 and world > 1:
         print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
 
-    B, H, S, D = WORKLOADS[args.workload]
+    key = args.workload
+    B, H, S, D = WORKLOADS[key]
+    prec = PRECISION_OF[key]
     BH_global = B * H * world
     bh0, cnt = fa2_b200.partition(BH_global, world, rank)        # this rank's slab range of the global batch
     assert cnt == B * H
@@ -233,15 +293,28 @@ def main():
     outs = (torch.empty_like(q), torch.empty(B, H, S, device="cuda"), torch.empty_like(q), torch.empty_like(q), torch.empty_like(q))
     lib = fa2_b200.load()
     st = torch.cuda.current_stream()
+    n = B * H * S * D
+    # small workloads fit in the 126 MB L2: flush it between timed iterations (outside the per-kernel event spans)
+    footprint = 9 * n * 4
+    flush = torch.empty(192 << 20, dtype=torch.uint8, device="cuda") if footprint < (160 << 20) else None
 
     def step():
-        fa2_b200.forward_backward(q, k, v, do, out=outs)
+        if flush is not None:
+            flush.fill_(1)
+        fa2_b200.forward_backward(q, k, v, do, precision=prec, out=outs)
 
     def barrier():
         torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def all_max(x):
+        if dist is None:
+            return x
+        t_ = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+        return float(t_.item())
 
     for _ in range(args.warmup):
         step()
@@ -262,47 +335,54 @@ def main():
     kn = (ctypes.c_int * 4)(0, 0, 0, 0)
     lib.fa2_profile_read(kms, kn)
     lib.fa2_profile_enable(0)
-    if dist is not None:
-        t = torch.tensor([ms_total], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
+    ms_total = all_max(ms_total)
     ms_step = ms_total / args.steps
+    if flush is not None:
+        # the L2 flush is not part of the path: the step time is the sum of the library's own kernel spans
+        ms_step = all_max(sum(kms[i] for i in range(4)) / args.steps)
     f_fwd, f_bwd = flops(B, H, S, D)
     value = (f_fwd + f_bwd) * world / (ms_step * 1e-3) / 1e12
 
+    # ---- the TIMED outputs against float64 on sampled slabs (first / middle / last work items)
+    verify = None
+    if not args.no_verify:
+        picks, err, finite = verify_outputs(q, k, v, do, outs)
+        err = {n_: all_max(e_) for n_, e_ in err.items()}
+        ok = all_max(0.0 if finite else 1.0) == 0.0 and all(err[n_] <= TOL[n_] for n_ in TOL)
+        verify = {"checked": "outputs of the last timed step vs float64", "slabs_per_rank": picks, "max_abs_err": err,
+                  "tol": TOL, "finite": finite, "ok": ok}
+
     # ---- end to end through the host-pointer C ABI (pinned host buffers, H2D + D2H inside the timed region)
-    n = B * H * S * D
     kernel_ms = ctypes.c_float(0)
     P = lambda t_: ctypes.c_void_p(t_.data_ptr())
+    PREC = fa2_b200._lib.PRECISION[prec]
     e2e_val = None
     t_e2e = float("inf")          # a rank that cannot run the leg reports inf; every rank still joins the collectives
-
-    def all_max(x):
-        if dist is None:
-            return x
-        t_ = torch.tensor([x], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t_, op=dist.ReduceOp.MAX)
-        return float(t_.item())
-
+    host = None
     try:
         hq, hk, hv, hdo = (torch.randn(B, H, S, D).pin_memory() for _ in range(4))
         ho, hdq, hdk, hdv = (torch.empty(B, H, S, D).pin_memory() for _ in range(4))
         hl = torch.empty(B, H, S).pin_memory()
+        host = (hq, hk, hv, hdo, ho, hl, hdq, hdk, hdv)
 
-        def e2e_step():
+        def e2e_step(n_gpus=1):
             fa2_b200._lib.check(lib.fa2_host_forward_backward(P(hq), P(hk), P(hv), P(hdo), P(ho), P(hl), P(hdq), P(hdk),
-                                                              P(hdv), B, H, S, D, 1, 1, ctypes.byref(kernel_ms)))
+                                                              P(hdv), B, H, S, D, PREC, n_gpus, ctypes.byref(kernel_ms)))
+            return kernel_ms.value
         e2e_step()
         ready = 0.0
     except (fa2_b200.FA2Error, RuntimeError, MemoryError) as ex:
         print("e2e leg unavailable on rank %d: %s" % (rank, ex), file=sys.stderr)
         ready = 1.0
+    e2e_kernel_ms = None
     if all_max(ready) == 0.0:     # (doubles as the barrier before the timed region)
         try:
             t0 = time.perf_counter()
+            kk = 0.0
             for _ in range(args.e2e_steps):
-                e2e_step()
+                kk += e2e_step()
             t_e2e = (time.perf_counter() - t0) / args.e2e_steps
+            e2e_kernel_ms = kk / args.e2e_steps
         except fa2_b200.FA2Error as ex:
             print("e2e failed on rank %d: %s" % (rank, ex), file=sys.stderr)
         t_e2e = all_max(t_e2e)
@@ -311,59 +391,144 @@ def main():
     h2d = 4 * n * 4
     d2h = 4 * n * 4 + B * H * S * 4
 
+    # PCIe ceiling with every rank copying at once (pinned, both directions together): what e2e can reach at best
+    pcie = None
+    if host is not None:
+        try:
+            dbuf_in, dbuf_out = torch.empty_like(q), torch.empty_like(q)
+            s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(2):
+                with torch.cuda.stream(s_in):
+                    dbuf_in.copy_(hq, non_blocking=True)
+                with torch.cuda.stream(s_out):
+                    ho.copy_(dbuf_out, non_blocking=True)
+            torch.cuda.synchronize()
+            dt = all_max(time.perf_counter() - t0)
+            gbs = 2 * n * 4 / dt / 1e9
+            floor_ms = max(h2d, d2h) / (gbs * 1e9) * 1e3
+            pcie = {"duplex_gbs_per_direction_per_gpu": gbs, "ranks_copying_at_once": world,
+                    "e2e_floor_ms_per_step": floor_ms,
+                    "e2e_frac_of_floor": floor_ms / (t_e2e * 1e3) if t_e2e not in (0.0, float("inf")) else None}
+            del dbuf_in, dbuf_out
+        except RuntimeError as ex:
+            print("pcie probe failed on rank %d: %s" % (rank, ex), file=sys.stderr)
+
+    # ---- strong scaling of the product's partitioner: ONE workload-sized problem over N GPUs (rank 0 drives all of
+    # them through fa2_host_forward_backward; the other ranks wait on a host-side barrier with their GPUs idle)
+    strong = None
+    if world > 1 and not args.no_strong and host is not None:
+        torch.cuda.synchronize()
+        dist.barrier(group=host_group)
+        if rank == 0:
+            try:
+                def timed(n_gpus, reps=3):
+                    e2e_step(n_gpus)                                   # warm-up: arenas / streams of every device
+                    best_k, best_w = float("inf"), float("inf")
+                    for _ in range(reps):
+                        t0 = time.perf_counter()
+                        km = e2e_step(n_gpus)
+                        best_w = min(best_w, (time.perf_counter() - t0) * 1e3)
+                        best_k = min(best_k, km)
+                    return best_k, best_w
+                k1, w1 = timed(1)
+                ref = [t_.clone() for t_ in (ho, hl, hdq, hdk, hdv)]
+                kN, wN = timed(world)
+                diffs = {n_: float((a - b).abs().max()) for n_, a, b in zip(("O", "LSE", "dQ", "dK", "dV"), ref, (ho, hl, hdq, hdk, hdv))}
+                same = diffs["O"] == 0 and diffs["LSE"] == 0 and diffs["dK"] == 0 and diffs["dV"] == 0 and diffs["dQ"] <= 1e-5
+                n_items_fwd = (B * H // world) * ((S + 255) // 256)
+                strong = {"problem": f"ONE B{B} H{H} S{S} D{D} problem split over {world} GPUs by fa2_partition (bh slabs), host API",
+                          "kernel_ms": {"T1": k1, "TN": kN, "efficiency": k1 / (world * kN)},
+                          "wall_ms": {"T1": w1, "TN": wN, "efficiency": w1 / (world * wN)},
+                          "tflops_aggregate_kernel": (f_fwd + f_bwd) / (kN * 1e-3) / 1e12,
+                          "max_abs_diff_vs_1gpu": diffs, "equal_to_1gpu": same,
+                          "limiter": f"wave quantisation: {n_items_fwd} forward work items per GPU on 148 persistent CTAs "
+                                     f"= {n_items_fwd / 148:.2f} waves (per chunk of the host pipeline), plus per-chunk launch tails"}
+            except fa2_b200.FA2Error as ex:
+                strong = {"error": str(ex)}
+        dist.barrier(group=host_group)
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
     peak_burst, peak_sus, hbm, peak_src = measured_peaks()
-    bwd_ms = kms[3] / max(kn[3], 1)
-    fwd_ms = kms[1] / max(kn[1], 1)
+    cast_ms, fwd_ms, pre_ms, bwd_ms = (kms[i] / max(kn[i], 1) for i in range(4))
     traffic = traffic_fwd = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and key == "C":    # the ncu DRAM figures were captured on workload C only
         with open(tpath) as fh:
             tj = json.load(fh)
             traffic, traffic_fwd = tj.get("bwd_kernel_dram_bytes_per_launch"), tj.get("fwd_kernel_dram_bytes_per_launch")
-    if args.workload != "C":
-        traffic = traffic_fwd = None            # the ncu DRAM figures were captured on workload C only
-    achieved = f_bwd / (bwd_ms * 1e-3) / 1e12 if bwd_ms > 0 else None
+    tf_bwd = f_bwd / (bwd_ms * 1e-3) / 1e12 if bwd_ms > 0 else None
+    tf_fwd = f_fwd / (fwd_ms * 1e-3) / 1e12 if fwd_ms > 0 else None
+    by_fwd, by_bwd = compulsory_bytes(B, H, S, D)
+    # MEASURED_PEAKS: the burst figure is for a kernel timed in a short run, the sustained one for a seconds-long loop
+    loop_s = ms_total * 1e-3
+    peak = peak_sus if loop_s >= 2.0 else peak_burst
+    peak_name = "bf16_tflops_sustained" if loop_s >= 2.0 else "bf16_tflops (burst)"
+    intensity = f_bwd / by_bwd                               # FLOP per compulsory byte of the dominant kernel
+    ridge = peak_burst * 1e12 / (hbm * 1e9)
+    if intensity >= ridge:
+        roofline = {"bound": "tensor", "kernel": "fa2_bwd_kernel (dominant: %.0f %% of the step)" % (100.0 * bwd_ms / ms_step),
+                    "achieved": tf_bwd, "peak": peak, "unit": "TFLOP/s", "frac": tf_bwd / peak if tf_bwd else None,
+                    "traffic": traffic,
+                    "peak_source": f"MEASURED_PEAKS.json {peak_name} ({peak_src}); timed loop lasted {loop_s:.2f} s",
+                    "frac_of_burst_peak": tf_bwd / peak_burst if tf_bwd else None,
+                    "frac_of_sustained_peak": tf_bwd / peak_sus if tf_bwd else None,
+                    "frac_of_nominal_2250": tf_bwd / 2250 if tf_bwd else None,
+                    "algorithmic_flop_per_launch": f_bwd,
+                    "fwd_kernel": {"achieved": tf_fwd, "frac": tf_fwd / peak if tf_fwd else None,
+                                   "frac_of_burst_peak": tf_fwd / peak_burst if tf_fwd else None,
+                                   "frac_of_nominal_2250": tf_fwd / 2250 if tf_fwd else None, "traffic": traffic_fwd}}
+    else:
+        gbs = by_bwd / (bwd_ms * 1e-3) / 1e9 if bwd_ms > 0 else None
+        roofline = {"bound": "hbm", "kernel": "fa2_bwd_kernel (dominant: %.0f %% of the step)" % (100.0 * bwd_ms / ms_step),
+                    "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm if gbs else None, "traffic": None,
+                    "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_src})",
+                    "algorithmic_bytes_per_launch": by_bwd,
+                    "note": "intensity %.0f FLOP/B is below the ridge (%.0f): bandwidth/latency side of the roofline; "
+                            "ideal time at the HBM peak is %.2f us, so the launch is latency-bound" %
+                            (intensity, ridge, by_bwd / (hbm * 1e9) * 1e6),
+                    "tensor_side": {"achieved_tflops": tf_bwd, "frac_of_burst_peak": tf_bwd / peak_burst if tf_bwd else None},
+                    "fwd_kernel": {"achieved_gbs": by_fwd / (fwd_ms * 1e-3) / 1e9 if fwd_ms else None, "achieved_tflops": tf_fwd},
+                    "step_gbs": (by_fwd + by_bwd) / (ms_step * 1e-3) / 1e9}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16 operands / f32 accumulate (fp32 API tensors)", "data": "synthetic",
-        "config": {"workload": f"configs[2] B{B} H{H} S{S} D{D} fwd+bwd per GPU (global batch {B * world})",
+        "config": {"workload": workload_name(key, B, H, S, D) + f" per GPU (global batch {B * world})",
+                   "precision_flag": prec,
                    "parallelism": f"bh-shard x{world} (fa2_partition), no collective",
-                   "l2": "inputs (4 x %d MiB fp32) exceed the 126 MB L2" % (n * 4 >> 20),
-                   "timed_region": "fp32 device tensors in -> fp32 device tensors out: cast + fwd + bwd pre-pass + bwd"},
+                   "l2": ("inputs (4 x %d MiB fp32) exceed the 126 MB L2" % (n * 4 >> 20)) if flush is None else
+                         "L2 flushed (192 MiB write) before every step; step time = sum of the kernel spans",
+                   "timed_region": "fp32 device tensors in -> fp32 device tensors out: cast + fwd (+ fused bwd pre-pass) + bwd"},
         "clocks": clocks,
         "gpu_launches": int(sum(kn)),
-        "kernel_ms": {"cast_qkv": kms[0] / max(kn[0], 1), "fwd": fwd_ms, "bwd_prepass": kms[2] / max(kn[2], 1), "bwd": bwd_ms},
-        "tflops": {"fwd_kernel": f_fwd / (fwd_ms * 1e-3) / 1e12 if fwd_ms else None,
-                   "bwd_kernel": achieved,
-                   "frac_of_nominal_2250": {"fwd": f_fwd / (fwd_ms * 1e-3) / 1e12 / 2250 if fwd_ms else None,
-                                            "bwd": achieved / 2250 if achieved else None}},
-        # the kernels are timed inside a long back-to-back loop (clocks under sw_power_cap, see "clocks"), so the
-        # denominator is the SUSTAINED measured cuBLAS bf16 peak; the burst figure is given beside it
-        "roofline": {"bound": "tensor", "kernel": "fa2_bwd_kernel<128,false> (dominant: %.0f %% of the step)" % (100.0 * bwd_ms / ms_step),
-                     "achieved": achieved, "peak": peak_sus, "unit": "TFLOP/s", "frac": achieved / peak_sus if achieved else None,
-                     "traffic": traffic,
-                     "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_src}); kernel timed inside the {args.steps}-step loop",
-                     "frac_of_burst_peak": achieved / peak_burst if achieved else None, "burst_peak": peak_burst,
-                     "algorithmic_flop_per_launch": f_bwd,
-                     "secondary_limit": "fp32 reduce-add of dQ into L2: 64 KB per 128x128 tile pair at ~24 B/clk/SM (tools/reduce_probe.cu)",
-                     "fwd_kernel": {"achieved": f_fwd / (fwd_ms * 1e-3) / 1e12 if fwd_ms else None,
-                                    "frac": (f_fwd / (fwd_ms * 1e-3) / 1e12) / peak_sus if fwd_ms else None,
-                                    "frac_of_burst_peak": (f_fwd / (fwd_ms * 1e-3) / 1e12) / peak_burst if fwd_ms else None,
-                                    "traffic": traffic_fwd}},
+        "kernel_ms": {"cast_qkv": cast_ms, "fwd": fwd_ms, "bwd_prepass": pre_ms, "bwd": bwd_ms},
+        "tflops": {"fwd_kernel": tf_fwd, "bwd_kernel": tf_bwd, "step_of_burst_peak": value / world / peak_burst,
+                   "step_of_nominal_2250": value / world / 2250},
+        "roofline": roofline,
+        "verify": verify,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "api": "fa2_host_forward_backward (C ABI, pinned host buffers)", "steps": args.e2e_steps},
+                "api": "fa2_host_forward_backward (C ABI, pinned host buffers)", "steps": args.e2e_steps,
+                "ms_per_step": t_e2e * 1e3 if t_e2e != float("inf") else None,
+                "per_gpu": e2e_val / world if e2e_val else None, "kernel_ms_inside": e2e_kernel_ms, "pcie": pcie},
     }
+    if strong is not None:
+        line["strong_scaling"] = strong
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(B, H, S, D)
     print(json.dumps(line))
+    sys.stdout.flush()
     if dist is not None:
         dist.destroy_process_group()
+    bad = (verify is not None and not verify["ok"]) or (strong is not None and not strong.get("equal_to_1gpu", False))
+    if bad:
+        print("bench.py: OUTPUT CHECK FAILED: " + json.dumps({"verify": verify, "strong": strong}), file=sys.stderr)
+        sys.exit(1)
 
 
 if __name__ == "__main__":

@@ -8,6 +8,7 @@
 #include "../../include/fa2_b200.h"
 #include "fa2_common.h"
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdlib>
 #include <cstdio>
@@ -193,16 +194,21 @@ int prepare(Prepared* pr, int B, int H, int S, int D, int precision, bool backwa
 }
 
 // optional per-kernel timing (fa2_profile_enable / fa2_profile_read)
-bool g_profile = false;
+std::atomic<bool> g_profile{false};
 struct ProfSpan { int kind; cudaEvent_t a, b; };
+std::mutex g_prof_mu;                      // guards g_spans (the host entry points launch from one thread per device)
 std::vector<ProfSpan> g_spans;
 struct ProfScope {
     int kind; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr; bool on;
-    ProfScope(int k, cudaStream_t s) : kind(k), st(s), on(g_profile) {
+    ProfScope(int k, cudaStream_t s) : kind(k), st(s), on(g_profile.load(std::memory_order_relaxed)) {
         if (on) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, st); }
     }
     ~ProfScope() {
-        if (on) { cudaEventRecord(b, st); g_spans.push_back({kind, a, b}); }
+        if (on) {
+            cudaEventRecord(b, st);
+            std::lock_guard<std::mutex> lk(g_prof_mu);
+            g_spans.push_back({kind, a, b});
+        }
     }
 };
 
@@ -225,7 +231,7 @@ int fuse_mask() {
 // dO / dQ non-null = fused forward+backward: the forward kernel also writes the 16-bit dO copy, D_i, LSE*log2(e)
 // and zero-fills dQ, so no separate backward pre-pass is launched.
 int run_fwd_main(const Prepared& pr, float* O, float* LSE, cudaStream_t st, const float* dO = nullptr,
-                 float* dQ = nullptr) {
+                 float* dQ = nullptr, int mask = 0) {
     FwdParams p{};
     int rc;
     if ((rc = make_tmap_16(&p.tm_q, pr.work + pr.wl.off_q, pr.BH, pr.S, pr.DP, 128, pr.bf16))) return rc;
@@ -235,8 +241,7 @@ int run_fwd_main(const Prepared& pr, float* O, float* LSE, cudaStream_t st, cons
     p.O = O; p.LSE = LSE; p.BH = pr.BH; p.S = pr.S; p.D = pr.D;
     p.scale = pr.scale; p.scale_log2 = pr.scale_log2; p.bf16 = pr.bf16;
     p.timeline = g_timeline;
-    if (dO && dQ) {
-        const int mask = fuse_mask();
+    if (dO && dQ && mask) {
         p.dO = dO;
         if (mask & 1) { p.dOh = pr.work + pr.wl.off_do; p.dQ_zero = dQ; }
         if (mask & 2) {
@@ -294,7 +299,9 @@ struct HostJob {
 // overlap (PCIe is full duplex; the reference does malloc -> H2D -> kernel -> D2H -> free serially,
 // kernels/kernel_fa2_optimized.cu:371-421).
 // Streams and events of the host pipeline, kept per device between calls (creating ~60 of them costs ~0.7 ms per
-// call).  A second concurrent call on the same device finds the set busy and builds a private one.
+// call).  PipeSet::mu is THE per-device lock of the host-pointer entry points: it is held for a whole call and covers
+// the streams, the events and both arenas (g_io / g_work) of the device, so two concurrent fa2_host_* calls that
+// land on the same device run one after the other.  Lock order everywhere: PipeSet::mu, then g_mu.
 constexpr int kSets = 3;     // device buffer sets of the host pipeline (H2D of c+1, kernels of c, D2H of c-1 and its tail)
 struct PipeSet {
     std::mutex mu;
@@ -341,32 +348,65 @@ struct PipeSet {
 };
 PipeSet g_pipes[kMaxDevices];
 
+// Chunk sizes (in slabs) of one device's share.  PCIe is full duplex (measured 2 x 47 GB/s against 55 GB/s one way),
+// so the job takes (bytes one way) / 47 GB/s plus whatever time only one direction is busy: the H2D of the first
+// chunk and, at the end, the D2H of whatever is still on the device when the last H2D finishes -- hence ~32 chunks.
+// The kernels are persistent (one CTA per SM, work items round-robin), so a chunk costs ceil(items / SMs) rounds of
+// one item each whatever its size: the chunk size is picked so that both passes fill their last round (>= 95 % of
+// the SM slots when a size in reach does), otherwise the sum of the per-chunk kernel spans -- what the CLI prints as
+// "Kernel execution completed" (src/main.cpp:107) -- is inflated by idle SMs.
+std::vector<int> plan_chunks(int count, int S, bool fwd, bool bwd, int n_sm = 148) {
+    std::vector<int> sizes;
+    if (count <= 0) return sizes;
+    const int items_f = (S + 255) / 256, items_b = (S + 127) / 128;     // work items per slab (forward / backward kernel)
+    auto eff = [&](int c) {
+        double e = 1.0;
+        for (int pass = 0; pass < 2; ++pass) {
+            if (pass == 0 ? !fwd : !bwd) continue;
+            const long long items = static_cast<long long>(c) * (pass == 0 ? items_f : items_b);
+            const long long slots = (items + n_sm - 1) / n_sm * n_sm;
+            const double x = static_cast<double>(items) / static_cast<double>(slots);
+            if (x < e) e = x;
+        }
+        return e;
+    };
+    int lo = (count + 31) / 32;
+    const int min_bh = (n_sm + items_b - 1) / items_b;                 // never so small that a chunk cannot fill the SMs
+    if (lo < min_bh) lo = min_bh;
+    if (lo > count) lo = count;
+    int hi = 2 * lo + 8;
+    if (hi > count) hi = count;
+    int best = lo;
+    double best_e = eff(lo);
+    for (int c = lo; c <= hi && best_e < 0.95; ++c) {
+        const double e = eff(c);
+        if (e >= 0.95 || e > best_e + 1e-9) { best = c; best_e = e; }
+    }
+    int left = count;
+    while (left > 0) { const int c = left < best ? left : best; sizes.push_back(c); left -= c; }
+    return sizes;
+}
+
 int host_worker(const HostJob& job, int dev, int bh0, int count, float* ms_out, std::string* err_out) {
+    if (dev < 0 || dev >= kMaxDevices) { *err_out = "device ordinal out of range"; return FA2_ERR_UNSUPPORTED; }
+    // Serialise host calls per device: the arenas and the cached streams belong to one call at a time.
+    std::lock_guard<std::mutex> device_lock(g_pipes[dev].mu);
+    PipeSet& ps = g_pipes[dev];
+    // Whatever way run() is left, nothing may still be in flight on the buffers the next call will reuse.
+    struct Drain {
+        PipeSet& s;
+        ~Drain() {
+            if (!s.ready) return;
+            cudaStreamSynchronize(s.s_in); cudaStreamSynchronize(s.s_comp); cudaStreamSynchronize(s.s_out);
+        }
+    } drain{ps};
     auto run = [&]() -> int {
         FA2_CUDA(cudaSetDevice(dev));
         const size_t slab = static_cast<size_t>(job.S) * job.D;           // floats per (b,h)
         const bool fwd = job.mode != FA2_MODE_BACKWARD, bwd = job.mode != FA2_MODE_FORWARD;
-        // chunk size: ~32 chunks per device, but never so small that a chunk cannot fill the SMs.  PCIe is full
-        // duplex (measured 2 x 47 GB/s against 55 GB/s one way), so the job takes (bytes one way) / 47 GB/s plus
-        // whatever time only one direction is busy: the H2D of the first chunk and, at the end, the D2H of
-        // everything still on the device when the last H2D finishes (about 1.25 chunks: the D2H of a chunk cannot
-        // start before its kernels, which cannot start before its H2D).  Hence small chunks (the kernels of a chunk
-        // take a fifth of its transfer time, so their efficiency does not matter here) and a short ramp
-        // (1/4, 1/2 of a chunk) at both ends.
-        const int tiles = (job.S + 127) / 128;
-        int chunk_bh = (count + 31) / 32;
-        const int min_bh = (2 * 148 + tiles - 1) / tiles;
-        if (chunk_bh < min_bh) chunk_bh = min_bh;
-        if (chunk_bh > count) chunk_bh = count;
-        std::vector<int> sizes;
-        {
-            int left = count;
-            const bool ramp = chunk_bh >= 4 && count >= 4 * chunk_bh;
-            const int r1 = chunk_bh / 4, r2 = chunk_bh / 2;
-            if (ramp) { sizes.push_back(r1); sizes.push_back(r2); left -= 2 * (r1 + r2); }
-            while (left > 0) { const int c = left < chunk_bh ? left : chunk_bh; sizes.push_back(c); left -= c; }
-            if (ramp) { sizes.push_back(r2); sizes.push_back(r1); }
-        }
+        std::vector<int> sizes = plan_chunks(count, job.S, fwd, bwd);
+        int chunk_bh = 0;
+        for (int c : sizes) chunk_bh = c > chunk_bh ? c : chunk_bh;
         const int n_chunks = static_cast<int>(sizes.size());
         const size_t tb = align_up(slab * chunk_bh * 4, 1024), lb = align_up(static_cast<size_t>(job.S) * chunk_bh * 4, 1024);
         const size_t set_bytes = 4 * tb + lb + (bwd ? 4 * tb : 0);       // Q K V O LSE [dO dQ dK dV]
@@ -379,10 +419,6 @@ int host_worker(const HostJob& job, int dev, int bh0, int count, float* ms_out, 
             FA2_CUDA(warm_fwd());
             FA2_CUDA(warm_bwd());
         }
-        PipeSet local_set;                                  // only used when the device's cached set is busy
-        std::unique_lock<std::mutex> pipe_lock(g_pipes[dev].mu, std::try_to_lock);
-        PipeSet& ps = pipe_lock.owns_lock() ? g_pipes[dev] : local_set;
-        struct LocalGuard { PipeSet& s; bool on; ~LocalGuard() { if (on) s.destroy(); } } guard{local_set, !pipe_lock.owns_lock()};
         FA2_CUDA(ps.init());
         FA2_CUDA(ps.grow(static_cast<size_t>(n_chunks)));
         cudaStream_t s_in = ps.s_in, s_comp = ps.s_comp, s_out = ps.s_out;
@@ -555,6 +591,14 @@ int fa2_partition(int BH, int n_parts, int part, int* bh0, int* count) {
     return FA2_OK;
 }
 
+int fa2_plan_chunks(int count, int S, int mode, int* sizes, int max_chunks) {
+    if (count < 0 || S <= 0 || mode < FA2_MODE_FORWARD || mode > FA2_MODE_FORWARD_BACKWARD || (!sizes && max_chunks > 0))
+        return -1;
+    const std::vector<int> v = plan_chunks(count, S, mode != FA2_MODE_BACKWARD, mode != FA2_MODE_FORWARD);
+    for (size_t i = 0; i < v.size() && static_cast<int>(i) < max_chunks; ++i) sizes[i] = v[i];
+    return static_cast<int>(v.size());
+}
+
 int fa2_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) {
@@ -605,11 +649,12 @@ int fa2_debug_set_timeline(void* dev_ptr) {
 #endif
 
 int fa2_profile_enable(int on) {
-    g_profile = on != 0;
+    g_profile.store(on != 0);
     return FA2_OK;
 }
 
 int fa2_profile_read(float* ms, int* launches) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     for (const ProfSpan& sp : g_spans) {
         float t = 0.f;
         if (cudaEventSynchronize(sp.b) == cudaSuccess && cudaEventElapsedTime(&t, sp.a, sp.b) == cudaSuccess) {
@@ -624,17 +669,15 @@ int fa2_profile_read(float* ms, int* launches) {
 }
 
 int fa2_release_workspaces(void) {
-    std::lock_guard<std::mutex> lk(g_mu);
     int prev = 0;
     if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); return FA2_OK; }
     for (int d = 0; d < kMaxDevices; ++d) {
-        {
-            std::lock_guard<std::mutex> pl(g_pipes[d].mu);
-            if (g_pipes[d].ready) {
-                cudaSetDevice(d);
-                cudaDeviceSynchronize();
-                g_pipes[d].destroy();
-            }
+        std::lock_guard<std::mutex> pl(g_pipes[d].mu);      // waits for a host call in flight on this device
+        std::lock_guard<std::mutex> lk(g_mu);                // same order as host_worker -> arena_reserve
+        if (g_pipes[d].ready) {
+            cudaSetDevice(d);
+            cudaDeviceSynchronize();
+            g_pipes[d].destroy();
         }
         for (Arena* a : {&g_work[d], &g_io[d]}) {
             if (a->ptr) {
@@ -690,10 +733,11 @@ int fa2_forward_backward(const float* Q, const float* K, const float* V, const f
     // zero-fill dQ in the shadow of the tensor-core loop, its epilogue forms D_i and LSE*log2(e).
     if ((rc = run_cast(pr, Q, K, V, st))) return rc;           // one 16-bit copy serves both passes
     {
-        const int mask = fuse_mask();
-        if (mask == 0) {
-            if ((rc = run_fwd_main(pr, O, LSE, st))) return rc;
-        } else if ((rc = run_fwd_main(pr, O, LSE, st, dO, dQ))) return rc; // also prepares dO(16 bit), D_i, LSE*log2e, dQ = 0
+        int mask = fuse_mask();
+        // the fused forward reads dO rows with 256-bit loads (ldg256_stream): a dO view that is only 16-byte aligned
+        // goes through the stand-alone pre-pass instead
+        if (reinterpret_cast<uintptr_t>(dO) & 31u) mask = 0;
+        if ((rc = run_fwd_main(pr, O, LSE, st, dO, dQ, mask))) return rc;  // mask != 0: also prepares dO(16 bit) / D_i, LSE*log2e / dQ = 0
         if (mask != 3 && (rc = run_bwd_prepass(pr, O, dO, LSE, dQ, 3 & ~mask, st))) return rc;
     }
     return run_bwd_main(pr, dQ, dK, dV, st);

@@ -25,8 +25,10 @@
 //                          tensor cycles of the five GEMMs -- so only the drain warps ever wait for it.
 //   16 MMA issuer, 17 TMA producer (also stages LSE and D_i per Q tile), 18-19 register donors.
 // The CTA launches with 640 x 96 registers; setmaxnreg moves them to compute 128 / drain 88 / rest 40.
-// Padding needs no masks: TMA zero-fills out-of-range Q/K/V/dO rows, out-of-range LSE is
-// staged as +inf (P = 0), and out-of-range dK/dV rows are not stored.
+// Padding: TMA zero-fills out-of-range Q/K/V/dO rows, out-of-range LSE (padded Q columns) is staged as
+// +inf (P = 0), out-of-range dK/dV rows are not stored, and padded KV lanes (kv row >= S, where S^T = 0 and
+// P = 2^(-lse) can overflow 16 bit for strongly negative LSE) are forced to P = dS = 0 by the compute
+// warps, so that no inf * 0 reaches the dQ contraction over the KV rows.
 #include "fa2_common.h"
 #include "ptx.cuh"
 
@@ -339,6 +341,8 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
         for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
         const int bh = w / n_tiles, kv_row0 = (w % n_tiles) * BT;
         const int G0 = it * n_tiles;
+        const bool ragged_kv = kv_row0 + BT > p.S;                          // CTA-uniform: only the last KV tile of a slab
+        const uint32_t kv_keep = (kv_row0 + n < p.S) ? 0xffffffffu : 0u;   // padded KV lane: P = dS = 0
 #ifdef FA2_TIMELINE
         if (threadIdx.x == 0 && p.timeline) {
             uint32_t smid;
@@ -384,6 +388,10 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
                     }
                 }
             }
+            if (ragged_kv) {
+#pragma unroll
+                for (int x = 0; x < 32; ++x) pk[x] &= kv_keep;
+            }
             tmem_st32(tS, pk);                                  // over the S columns this thread already consumed
             tmem_wait_st();
             tc_fence_before();
@@ -428,6 +436,7 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
                             w[u * 2] = BF16 ? mul_bf16x2(p0, pack_bf16x2(t0.x, t0.y)) : mul_half2(p0, pack_half2(t0.x, t0.y));
                             w[u * 2 + 1] = BF16 ? mul_bf16x2(p1, pack_bf16x2(t1.x, t1.y)) : mul_half2(p1, pack_half2(t1.x, t1.y));
                         }
+                        if (ragged_kv) { w[0] &= kv_keep; w[1] &= kv_keep; w[2] &= kv_keep; w[3] &= kv_keep; }
                         *reinterpret_cast<uint4*>(ds_atom + swz128(n, sub * 4 + c8)) = make_uint4(w[0], w[1], w[2], w[3]);
                     }
                 }

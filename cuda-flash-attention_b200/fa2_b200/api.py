@@ -23,30 +23,89 @@ from ._lib import FA2Error, MODE, PRECISION, check
 SUPPORTED_HEAD_DIMS = (32, 64, 128)
 
 
+def _is_cupy(x) -> bool:
+    return hasattr(x, "data") and hasattr(x.data, "ptr") and not hasattr(x, "data_ptr")
+
+
 def _ptr(x) -> int:
     """Raw device pointer of a torch CUDA tensor or a CuPy array."""
     if hasattr(x, "data_ptr"):
         return x.data_ptr()
-    if hasattr(x, "data") and hasattr(x.data, "ptr"):
+    if _is_cupy(x):
         return x.data.ptr
     raise TypeError(f"cannot take a device pointer from {type(x)!r}")
 
 
-def _stream_ptr(stream=None) -> int:
+def _stream_ptr(stream=None, like=None) -> int:
+    """cudaStream_t of `stream` (torch / CuPy stream object or a raw handle); None = the current stream of the
+    framework that owns `like` (torch is imported only for torch tensors)."""
     if stream is not None:
         return int(getattr(stream, "cuda_stream", getattr(stream, "ptr", stream)))
+    if like is not None and _is_cupy(like):
+        import cupy
+        return int(cupy.cuda.get_current_stream().ptr)
     import torch
     return torch.cuda.current_stream().cuda_stream
 
 
-def _check_dev(*tensors):
-    import torch
-    for t in tensors:
-        if isinstance(t, torch.Tensor):
+def _device_of(x) -> int:
+    if hasattr(x, "data_ptr"):
+        return x.device.index if x.device.index is not None else 0
+    return int(x.device.id)                               # CuPy
+
+
+def _check_dev(shape4, **tensors):
+    """Every tensor must be a contiguous float32 device array on ONE device: [B,H,S,D] like Q, or [B,H,S]
+    for the logsumexp.  Anything else would be an out-of-bounds device access inside the library."""
+    dev = None
+    for name, t in tensors.items():
+        want = tuple(shape4[:3]) if name in ("LSE", "logsumexp") else tuple(shape4)
+        if hasattr(t, "data_ptr"):                        # torch
+            import torch
             if not t.is_cuda:
-                raise ValueError("device entry points take CUDA tensors (use host_* for numpy arrays)")
-            if t.dtype != torch.float32 or not t.is_contiguous():
-                raise ValueError("tensors must be contiguous float32 [B,H,S,D]")
+                raise ValueError(f"{name}: device entry points take CUDA tensors (use run_flash_attention for numpy arrays)")
+            ok = t.dtype == torch.float32 and t.is_contiguous()
+        elif _is_cupy(t):
+            ok = str(t.dtype) == "float32" and bool(t.flags.c_contiguous)
+        else:
+            raise TypeError(f"{name}: expected a torch CUDA tensor or a CuPy array, got {type(t)!r}")
+        if not ok:
+            raise ValueError(f"{name} must be contiguous float32")
+        if tuple(t.shape) != want:
+            raise ValueError(f"{name} has shape {tuple(t.shape)}, expected {want}")
+        d = _device_of(t)
+        if dev is None:
+            dev = d
+        elif d != dev:
+            raise ValueError(f"{name} lives on device {d}, Q on device {dev}")
+    return dev
+
+
+class _on_device:
+    """Make `dev` current for the duration of the call (cudaSetDevice via the owning framework)."""
+
+    def __init__(self, like, dev):
+        self.like, self.dev, self.ctx = like, dev, None
+
+    def __enter__(self):
+        if _is_cupy(self.like):
+            import cupy
+            self.ctx = cupy.cuda.Device(self.dev)
+        else:
+            import torch
+            self.ctx = torch.cuda.device(self.dev)
+        return self.ctx.__enter__()
+
+    def __exit__(self, *a):
+        return self.ctx.__exit__(*a)
+
+
+def _empty_like(x, shape=None):
+    if _is_cupy(x):
+        import cupy
+        return cupy.empty(tuple(x.shape) if shape is None else shape, dtype=cupy.float32)
+    import torch
+    return torch.empty(tuple(x.shape) if shape is None else shape, device=x.device, dtype=torch.float32)
 
 
 def partition(BH: int, n_parts: int, part: int) -> Tuple[int, int]:
@@ -58,41 +117,43 @@ def partition(BH: int, n_parts: int, part: int) -> Tuple[int, int]:
 
 def forward(Q, K, V, precision: str = "fp32", stream=None, out=None):
     """O, LSE = FA2 forward on device tensors [B,H,S,D] fp32. LSE is natural-log [B,H,S]."""
-    import torch
-    _check_dev(Q, K, V)
+    if len(Q.shape) != 4:
+        raise ValueError("Q must be [B,H,S,D]")
     B, H, S, D = Q.shape
-    O, LSE = out if out is not None else (torch.empty_like(Q), torch.empty((B, H, S), device=Q.device, dtype=torch.float32))
-    with torch.cuda.device(Q.device):
+    O, LSE = out if out is not None else (_empty_like(Q), _empty_like(Q, (B, H, S)))
+    dev = _check_dev(Q.shape, Q=Q, K=K, V=V, O=O, LSE=LSE)
+    with _on_device(Q, dev):
         check(_lib.load().fa2_forward(_ptr(Q), _ptr(K), _ptr(V), _ptr(O), _ptr(LSE), B, H, S, D,
-                                      PRECISION[precision], _stream_ptr(stream)))
+                                      PRECISION[precision], _stream_ptr(stream, Q)))
     return O, LSE
 
 
 def backward(Q, K, V, O, dO, LSE, precision: str = "fp32", stream=None, out=None):
     """dQ, dK, dV = FA2 backward. D_i = rowsum(dO*O) and the dQ zero-fill happen inside."""
-    import torch
-    _check_dev(Q, K, V, O, dO, LSE)
+    if len(Q.shape) != 4:
+        raise ValueError("Q must be [B,H,S,D]")
     B, H, S, D = Q.shape
-    dQ, dK, dV = out if out is not None else (torch.empty_like(Q), torch.empty_like(Q), torch.empty_like(Q))
-    with torch.cuda.device(Q.device):
+    dQ, dK, dV = out if out is not None else (_empty_like(Q), _empty_like(Q), _empty_like(Q))
+    dev = _check_dev(Q.shape, Q=Q, K=K, V=V, O=O, dO=dO, LSE=LSE, dQ=dQ, dK=dK, dV=dV)
+    with _on_device(Q, dev):
         check(_lib.load().fa2_backward(_ptr(Q), _ptr(K), _ptr(V), _ptr(O), _ptr(dO), _ptr(LSE), _ptr(dQ), _ptr(dK),
-                                       _ptr(dV), B, H, S, D, PRECISION[precision], _stream_ptr(stream)))
+                                       _ptr(dV), B, H, S, D, PRECISION[precision], _stream_ptr(stream, Q)))
     return dQ, dK, dV
 
 
 def forward_backward(Q, K, V, dO, precision: str = "fp32", stream=None, out=None):
     """O, LSE, dQ, dK, dV in one call; O/LSE never leave the device between the passes."""
-    import torch
-    _check_dev(Q, K, V, dO)
+    if len(Q.shape) != 4:
+        raise ValueError("Q must be [B,H,S,D]")
     B, H, S, D = Q.shape
     if out is None:
-        out = (torch.empty_like(Q), torch.empty((B, H, S), device=Q.device, dtype=torch.float32),
-               torch.empty_like(Q), torch.empty_like(Q), torch.empty_like(Q))
+        out = (_empty_like(Q), _empty_like(Q, (B, H, S)), _empty_like(Q), _empty_like(Q), _empty_like(Q))
     O, LSE, dQ, dK, dV = out
-    with torch.cuda.device(Q.device):
+    dev = _check_dev(Q.shape, Q=Q, K=K, V=V, dO=dO, O=O, LSE=LSE, dQ=dQ, dK=dK, dV=dV)
+    with _on_device(Q, dev):
         check(_lib.load().fa2_forward_backward(_ptr(Q), _ptr(K), _ptr(V), _ptr(dO), _ptr(O), _ptr(LSE), _ptr(dQ),
                                                _ptr(dK), _ptr(dV), B, H, S, D, PRECISION[precision],
-                                               _stream_ptr(stream)))
+                                               _stream_ptr(stream, Q)))
     return O, LSE, dQ, dK, dV
 
 
@@ -130,7 +191,13 @@ def run_flash_attention(Q, K, V, O=None, logsumexp=None, dO=None, *, method: str
     if mode not in MODE:
         raise ValueError(f"unknown mode {mode!r}")
     Q = _host(Q, "Q"); K = _host(K, "K"); V = _host(V, "V")
+    if Q.ndim != 4:
+        raise ValueError("Q must be [B,H,S,D]")
     B, H, S, D = Q.shape
+    for name, a, want in (("K", K, Q.shape), ("V", V, Q.shape), ("O", O, Q.shape), ("dO", dO, Q.shape),
+                          ("logsumexp", logsumexp, (B, H, S))):
+        if a is not None and tuple(np.shape(a)) != tuple(want):
+            raise ValueError(f"{name} has shape {tuple(np.shape(a))}, expected {tuple(want)}")
     if D not in SUPPORTED_HEAD_DIMS:
         raise FA2Error(1, f"Error: Unsupported head dimension {D}")
     lib = _lib.load()

@@ -93,6 +93,12 @@ int fa2_host_forward_backward(const float* Q, const float* K, const float* V, co
  * over BH = B*H independent (batch, head) slabs.  Pure arithmetic, no GPU needed. */
 int fa2_partition(int BH, int n_parts, int part, int* bh0, int* count);
 
+/* The host pipeline's chunking of one device's share of `count` slabs (mode = FA2_MODE_*): writes up to
+ * max_chunks chunk sizes (in slabs, in processing order) and returns the number of chunks (-1 on bad
+ * arguments).  Chunk sizes are chosen so that the persistent kernels' last round of work items is full.
+ * Pure arithmetic, no GPU needed. */
+int fa2_plan_chunks(int count, int S, int mode, int* sizes, int max_chunks);
+
 /* Number of CUDA devices visible to the library (0 without a GPU; never fails). */
 int fa2_device_count(void);
 

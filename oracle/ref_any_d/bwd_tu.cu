@@ -25,3 +25,23 @@ extern "C" int ref_any_d_backward(const float* q, const float* k, const float* v
         default: return 2;
     }
 }
+
+// The reference's own backward host launcher (f-attn2-backward.cu:384-485) at any head dim; see fwd_tu.cu.
+template <int D>
+static int run_host_bwd(const float* q, const float* k, const float* v, const float* o, const float* go,
+                        const float* lse, float* dq, float* dk, float* dv, int B, int S, int H, TimerManager* tm) {
+    auto kern = flash_attention2_backward_kernel<32, 32, D>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(shm_t<32, 32, D>)) != cudaSuccess) return 1;
+    host_flash_attention2_backward<D>(q, k, v, o, go, lse, dq, dk, dv, B, S, H, tm);
+    return 0;
+}
+int ref_any_d_host_backward(const float* q, const float* k, const float* v, const float* o, const float* go,
+                            const float* lse, float* dq, float* dk, float* dv, int B, int H, int S, int D,
+                            TimerManager* tm) {
+    switch (D) {
+        case 32: return run_host_bwd<32>(q, k, v, o, go, lse, dq, dk, dv, B, S, H, tm);
+        case 64: return run_host_bwd<64>(q, k, v, o, go, lse, dq, dk, dv, B, S, H, tm);
+        case 128: return run_host_bwd<128>(q, k, v, o, go, lse, dq, dk, dv, B, S, H, tm);
+        default: return 2;
+    }
+}

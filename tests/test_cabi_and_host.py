@@ -154,3 +154,39 @@ def test_cli_short_file_is_an_error(tmp_path):
         np.zeros(10, np.float32).tofile(d / f"{n}.bin")
     r = run_cli("fa2", "forward", "fp32", str(d))
     assert r.returncode == 1 and "fread" in r.stderr                                 # utils.cpp:17
+
+
+def test_host_surface_rejects_mismatched_shapes_before_touching_the_library():
+    q = np.zeros((1, 2, 16, 64), np.float32)
+    with pytest.raises(ValueError, match="V has shape"):
+        fa2_b200.run_flash_attention(q, q, np.zeros((1, 2, 8, 64), np.float32))
+    with pytest.raises(ValueError, match="dO has shape"):
+        fa2_b200.run_flash_attention(q, q, q, dO=np.zeros((1, 2, 16, 32), np.float32), mode="forward_backward")
+    with pytest.raises(ValueError, match="logsumexp has shape"):
+        fa2_b200.run_flash_attention(q, q, q, O=q, logsumexp=np.zeros((1, 2, 15), np.float32), mode="backward")
+
+
+def test_device_surface_validates_every_tensor_on_cpu_tensors():
+    import torch
+    from fa2_b200 import api
+    x = torch.zeros(1, 1, 16, 64)
+    with pytest.raises(ValueError, match="CUDA tensors"):
+        api.forward(x, x, x)
+    with pytest.raises(TypeError):
+        api._check_dev((1, 1, 16, 64), Q=np.zeros((1, 1, 16, 64), np.float32))
+
+
+@pytest.mark.parametrize("count,S,mode", [(256, 4096, 2), (32, 4096, 2), (16, 16384, 2), (80, 1024, 2), (48, 4096, 0), (1, 100, 1), (7, 33, 2)])
+def test_plan_chunks_covers_the_share_and_fills_the_last_round(count, S, mode):
+    """Host pipeline chunking (fa2_plan_chunks): chunk sizes add up to the device's share, in order, and a full-size
+    chunk leaves at most ~5 % of the persistent kernels' SM slots idle whenever a size within reach can."""
+    lib = fa2_b200.load()
+    buf = (ctypes.c_int * 512)()
+    n = lib.fa2_plan_chunks(count, S, mode, buf, 512)
+    sizes = list(buf[:n])
+    assert n >= 1 and sum(sizes) == count and all(s > 0 for s in sizes)
+    assert all(s == sizes[0] for s in sizes[:-1]) and sizes[-1] <= sizes[0]
+    if count >= 64 and S == 4096:
+        items = sizes[0] * (S // 256)
+        assert items / (-(-items // 148) * 148) >= 0.95
+    assert lib.fa2_plan_chunks(-1, S, mode, buf, 512) == -1

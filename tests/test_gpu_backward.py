@@ -120,7 +120,7 @@ def test_host_api_backward_default_dO_is_ones(U):
 
 def test_host_api_chunked_pipeline_matches_device_api(U):
     """fa2_host_* streams the slabs through three buffer sets in chunks (H2D / kernels / D2H overlapped);
-    80 slabs of S=1024 make three chunks (37 + 37 + 6).  Results must equal the one-shot device path."""
+    80 slabs of S=1024 make three chunks (37 + 37 + 6, fa2_plan_chunks).  Results must equal the one-shot device path."""
     import torch
     import fa2_b200
     Q, K, V, dO = U.randn_case((1, 80, 1024, 64), seed=17)
@@ -134,9 +134,9 @@ def test_host_api_chunked_pipeline_matches_device_api(U):
     assert secs > 0
 
 
-def test_host_api_ramped_chunks_match_device_api(U):
-    """48 slabs of S=4096 are streamed as 2 + 5 + 10 + 10 + 10 + 4 + 5 + 2 (short chunks at both ends keep the
-    one-directional PCIe phases short); every slab must land where the one-shot device path puts it."""
+def test_host_api_many_chunks_match_device_api(U):
+    """48 slabs of S=4096 are streamed as 9 + 9 + 9 + 9 + 9 + 3 (fa2_plan_chunks: sizes that fill the persistent
+    kernels' last round); every slab must land where the one-shot device path puts it."""
     import torch
     import fa2_b200
     Q, K, V, dO = U.randn_case((1, 48, 4096, 64), seed=23)
@@ -249,3 +249,117 @@ def test_host_api_two_gpus_match_one_gpu(U):
             assert np.array_equal(a, b)
         else:
             assert U.maxerr(a, b) < 1e-5
+
+
+@pytest.mark.parametrize("shape", [(1, 2, 100, 64), (1, 2, 200, 128), (2, 1, 129, 32)], ids=lambda s: "B%d_H%d_S%d_D%d" % s)
+def test_backward_ragged_kv_tile_with_strongly_negative_lse(U, shape):
+    """Padded KV lanes of a ragged last tile see S^T = 0, so P = 2^(0 - lse2): with every score near -32 that is
+    ~e^32 / S, an fp16 inf, and inf * 0 (zero-filled K row) used to poison whole dQ rows with NaN.  The compute
+    warps now force P = dS = 0 in padded lanes."""
+    B, H, S, D = shape
+    rng = np.random.default_rng(77)
+    u = rng.standard_normal(D).astype(np.float32)
+    u *= np.sqrt(D) / np.linalg.norm(u)                                  # |u|^2 = D
+    Q = (u + 0.05 * rng.standard_normal(shape)).astype(np.float32)
+    K = (-4.0 * u + 0.05 * rng.standard_normal(shape)).astype(np.float32)   # scores ~ -4 sqrt(D): LSE << -10
+    V, dO = (rng.standard_normal(shape).astype(np.float32) for _ in range(2))
+    tO, tL, tdQ, tdK, tdV = U.orc.attention_fp64(Q, K, V, dO)
+    assert tL.max() < -10
+    dQ, dK, dV = U.gpu_backward(Q, K, V, tO.astype(np.float32), dO, tL.astype(np.float32))
+    for got, want, n in ((dQ, tdQ, "dQ"), (dK, tdK, "dK"), (dV, tdV, "dV")):
+        assert np.isfinite(got).all(), n
+        assert U.maxerr(got, want) < U.TOL_GRAD, n
+    import torch
+    import fa2_b200
+    outs = fa2_b200.forward_backward(*(U.dev(x) for x in (Q, K, V, dO)))
+    torch.cuda.synchronize()
+    for got, want, tol in zip(outs, (tO, tL, tdQ, tdK, tdV), (U.TOL_O, 5e-3, U.TOL_GRAD, U.TOL_GRAD, U.TOL_GRAD)):
+        assert torch.isfinite(got).all()
+        assert U.maxerr(U.host(got), want) < tol         # (|LSE| ~ 30 here: fp16 operand rounding scales with |score|)
+
+
+def test_fused_call_accepts_16_byte_aligned_dO_view(U):
+    """The fused forward reads dO rows with 256-bit loads; a dO view that is only 16-byte aligned must not fault:
+    the library routes it through the stand-alone pre-pass."""
+    import torch
+    import fa2_b200
+    shape = (1, 2, 300, 64)
+    Q, K, V, dO = U.randn_case(shape, seed=14)
+    buf = torch.zeros(dO.size + 4, device="cuda")
+    g = buf[4:].view(shape)                                # 16 bytes into a 256-byte aligned allocation
+    g.copy_(torch.from_numpy(dO))
+    assert g.data_ptr() % 32 == 16 and g.is_contiguous()
+    got = fa2_b200.forward_backward(U.dev(Q), U.dev(K), U.dev(V), g)
+    torch.cuda.synchronize()
+    want = U.orc.attention_fp64(Q, K, V, dO)
+    for x, w, tol in zip(got, want, (U.TOL_O, U.TOL_LSE, U.TOL_GRAD, U.TOL_GRAD, U.TOL_GRAD)):
+        assert U.maxerr(U.host(x), w) < tol
+
+
+def test_concurrent_host_calls_on_one_device_are_serialised(U):
+    """Two threads calling fa2_host_* on the same device share that device's arenas and streams: the library runs
+    them one after the other (per-device lock), so both get the right answer even with different sizes."""
+    import threading
+    import fa2_b200
+    cases = [U.randn_case((1, 6, 700, 64), seed=51), U.randn_case((2, 9, 1500, 128), seed=52),
+             U.randn_case((1, 3, 260, 32), seed=53), U.randn_case((1, 12, 1100, 64), seed=54)]
+    results = [None] * len(cases)
+
+    def work(i):
+        Q, K, V, dO = cases[i]
+        results[i] = fa2_b200.run_flash_attention(Q, K, V, dO=dO, mode="forward_backward")[0]
+
+    for _ in range(2):
+        th = [threading.Thread(target=work, args=(i,)) for i in range(len(cases))]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        for (Q, K, V, dO), got in zip(cases, results):
+            want = U.orc.attention_fp64(Q, K, V, dO)
+            for x, w, tol in zip(got, want, (U.TOL_O, U.TOL_LSE, U.TOL_GRAD, U.TOL_GRAD, U.TOL_GRAD)):
+                assert U.maxerr(x, w) < tol
+
+
+class _FakeCuPy:
+    """Duck-types the parts of a cupy.ndarray the binding touches (.data.ptr, .dtype, .flags, .shape, .device.id)
+    on top of a torch CUDA tensor -- CuPy itself is not in this image."""
+
+    class _Mem:
+        def __init__(self, ptr):
+            self.ptr = ptr
+
+    class _Flags:
+        c_contiguous = True
+
+    class _Dev:
+        def __init__(self, i):
+            self.id = i
+
+    def __init__(self, t):
+        self.t = t
+        self.data = self._Mem(t.data_ptr())
+        self.dtype = "float32"
+        self.flags = self._Flags()
+        self.shape = tuple(t.shape)
+        self.device = self._Dev(t.device.index or 0)
+
+
+def test_cupy_style_arrays_go_through_the_data_ptr_branch(U, monkeypatch):
+    """The harness of the reference passes CuPy arrays (test_flash_attention2.py:278-289): `.data.ptr` and an explicit
+    stream handle are all the binding needs."""
+    import torch
+    import fa2_b200
+    from fa2_b200 import api
+    Q, K, V, dO = U.randn_case((1, 2, 200, 64), seed=61)
+    tens = [U.dev(x) for x in (Q, K, V, dO)]
+    outs_t = [torch.empty_like(tens[0]), torch.empty(1, 2, 200, device="cuda"), torch.empty_like(tens[0]),
+              torch.empty_like(tens[0]), torch.empty_like(tens[0])]
+    monkeypatch.setattr(api, "_on_device", lambda like, dev: torch.cuda.device(dev))      # (no cupy.cuda.Device here)
+    q, k, v, g = (_FakeCuPy(t) for t in tens)
+    out = tuple(_FakeCuPy(t) for t in outs_t)
+    api.forward_backward(q, k, v, g, stream=torch.cuda.current_stream().cuda_stream, out=out)
+    torch.cuda.synchronize()
+    want = U.orc.attention_fp64(Q, K, V, dO)
+    for x, w, tol in zip(outs_t, want, (U.TOL_O, U.TOL_LSE, U.TOL_GRAD, U.TOL_GRAD, U.TOL_GRAD)):
+        assert U.maxerr(U.host(x), w) < tol
+    with pytest.raises(ValueError):
+        api.forward(q, k, _FakeCuPy(torch.empty(1, 2, 100, 64, device="cuda")), stream=0)
