@@ -62,8 +62,32 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
+// Descriptors are a pure function of (base, geometry, type): a small per-thread cache saves the 4 + 7 driver calls
+// per forward + backward call when the same tensors come back (training loops, the harness's timed repeats).
+struct TmapKey {
+    const void* base; int BH, S, D, kind;      // kind: 0 = fp16 copy, 1 = bf16 copy, 2 = fp32 tensor
+    bool operator==(const TmapKey& o) const { return base == o.base && BH == o.BH && S == o.S && D == o.D && kind == o.kind; }
+};
+struct TmapCache {
+    static constexpr int N = 32;
+    TmapKey key[N];
+    CUtensorMap map[N];
+    int used = 0, next = 0;
+    const CUtensorMap* find(const TmapKey& k) const {
+        for (int i = 0; i < used; ++i) if (key[i] == k) return &map[i];
+        return nullptr;
+    }
+    void put(const TmapKey& k, const CUtensorMap& m) {
+        const int i = used < N ? used++ : (next = (next + 1) % N);
+        key[i] = k; map[i] = m;
+    }
+};
+thread_local TmapCache g_tmaps;
+
 // 16-bit [BH][S][DP] tensor, box {64 cols, box_rows, 1 slab}, 128-byte swizzle, zero OOB fill.
 int make_tmap_16(CUtensorMap* tm, void* base, int BH, int S, int DP, int box_rows, int bf16) {
+    const TmapKey k{base, BH, S, DP, bf16 ? 1 : 0};
+    if (const CUtensorMap* hit = g_tmaps.find(k)) { *tm = *hit; return FA2_OK; }
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return fail(FA2_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
     cuuint64_t dims[3] = {static_cast<cuuint64_t>(DP), static_cast<cuuint64_t>(S), static_cast<cuuint64_t>(BH)};
@@ -74,11 +98,14 @@ int make_tmap_16(CUtensorMap* tm, void* base, int BH, int S, int DP, int box_row
                      strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(FA2_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    g_tmaps.put(k, *tm);
     return FA2_OK;
 }
 
 // fp32 [BH][S][D] tensor addressed by the dQ reduce-add: box {32 cols, 128 rows, 1 slab}, 128-byte swizzle.
 int make_tmap_f32(CUtensorMap* tm, void* base, int BH, int S, int D) {
+    const TmapKey k{base, BH, S, D, 2};
+    if (const CUtensorMap* hit = g_tmaps.find(k)) { *tm = *hit; return FA2_OK; }
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return fail(FA2_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
     cuuint64_t dims[3] = {static_cast<cuuint64_t>(D), static_cast<cuuint64_t>(S), static_cast<cuuint64_t>(BH)};
@@ -89,6 +116,7 @@ int make_tmap_f32(CUtensorMap* tm, void* base, int BH, int S, int D) {
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(FA2_ERR_CUDA, "cuTensorMapEncodeTiled(fp32) failed with CUresult %d", (int)r);
+    g_tmaps.put(k, *tm);
     return FA2_OK;
 }
 
@@ -104,7 +132,8 @@ std::mutex g_mu;
 Arena g_work[kMaxDevices];   // 16-bit operand copies, delta, lse_log2
 Arena g_io[kMaxDevices];     // fp32 device mirrors used by the host-pointer entry points
 
-int arena_reserve(Arena* arenas, int dev, size_t bytes, void** out) {
+// zero_head > 0: the first zero_head bytes are state that must start at zero (the work arena's RangeBlock).
+int arena_reserve(Arena* arenas, int dev, size_t bytes, void** out, size_t zero_head = 0) {
     std::lock_guard<std::mutex> lk(g_mu);
     Arena& a = arenas[dev];
     if (a.bytes < bytes) {
@@ -116,6 +145,7 @@ int arena_reserve(Arena* arenas, int dev, size_t bytes, void** out) {
         }
         FA2_CUDA(cudaMalloc(&a.ptr, bytes));
         a.bytes = bytes;
+        if (zero_head) FA2_CUDA(cudaMemset(a.ptr, 0, zero_head));     // (synchronous: ordered before any later launch)
     }
     *out = a.ptr;
     return FA2_OK;
@@ -130,7 +160,7 @@ WorkLayout work_layout(size_t rows, int DP, bool backward) {
     WorkLayout w{};
     const size_t t16 = align_up(rows * DP * 2, 1024);
     const size_t vec = align_up(rows * 4, 1024);
-    size_t off = 0;
+    size_t off = kRangeBytes;               // the RangeBlock sits at offset 0 whatever the shape
     w.off_q = off; off += t16;
     w.off_k = off; off += t16;
     w.off_v = off; off += t16;
@@ -171,6 +201,7 @@ struct Prepared {
     uint8_t* work = nullptr;
     WorkLayout wl{};
     float scale = 0.f, scale_log2 = 0.f;
+    RangeBlock* range() const { return reinterpret_cast<RangeBlock*>(work); }
 };
 
 int prepare(Prepared* pr, int B, int H, int S, int D, int precision, bool backward) {
@@ -185,7 +216,7 @@ int prepare(Prepared* pr, int B, int H, int S, int D, int precision, bool backwa
     pr->rows = static_cast<size_t>(pr->BH) * S;
     pr->wl = work_layout(pr->rows, pr->DP, backward);
     void* w = nullptr;
-    rc = arena_reserve(g_work, pr->dev, pr->wl.total, &w);
+    rc = arena_reserve(g_work, pr->dev, pr->wl.total, &w, kRangeBytes);
     if (rc) return rc;
     pr->work = static_cast<uint8_t*>(w);
     pr->scale = 1.0f / sqrtf(static_cast<float>(D));
@@ -217,7 +248,31 @@ unsigned long long* g_timeline = nullptr;   // set by fa2_debug_set_timeline (de
 int run_cast(const Prepared& pr, const float* Q, const float* K, const float* V, cudaStream_t st) {
     ProfScope prof(0, st);
     FA2_CUDA(launch_cast_qkv(Q, K, V, pr.work + pr.wl.off_q, pr.work + pr.wl.off_k, pr.work + pr.wl.off_v, pr.rows,
-                             pr.D, pr.DP, pr.bf16, st));
+                             pr.D, pr.DP, pr.bf16, pr.range(), pr.scale, pr.scale_log2, st));
+    // the cast's last block has decided the scales; re-cast only what does not fit fp16 as it is
+    FA2_CUDA(launch_range_fix_qkv(Q, K, V, pr.work + pr.wl.off_q, pr.work + pr.wl.off_k, pr.work + pr.wl.off_v, pr.rows,
+                                  pr.D, pr.DP, pr.bf16, pr.range(), st));
+    return FA2_OK;
+}
+
+// Problems of a few MB per tensor: one cooperative launch does amax + scale decision + cast (+ dO cast and dQ
+// zero-fill when dO is given) -- the always-launched re-cast kernels would cost more than the cast itself there.
+constexpr size_t kSmallElems = size_t(2) << 20;          // 16-bit elements per tensor
+bool is_small(const Prepared& pr) { return pr.rows * pr.DP <= kSmallElems; }
+
+int run_cast_small(const Prepared& pr, const float* Q, const float* K, const float* V, const float* dO, float* dQ,
+                   cudaStream_t st) {
+    ProfScope prof(0, st);
+    FA2_CUDA(launch_cast_small(Q, K, V, dO, pr.work + pr.wl.off_q, pr.work + pr.wl.off_k, pr.work + pr.wl.off_v,
+                               dO ? pr.work + pr.wl.off_do : nullptr, dQ, pr.rows, pr.D, pr.DP, pr.bf16, pr.range(),
+                               pr.scale, pr.scale_log2, sm_count_current(), st));
+    return FA2_OK;
+}
+
+// after the dO cast (pre-pass or the forward's donor warps), before the backward kernel
+int run_fix_do(const Prepared& pr, const float* dO, cudaStream_t st) {
+    ProfScope prof(2, st);
+    FA2_CUDA(launch_range_fix_do(dO, pr.work + pr.wl.off_do, pr.rows, pr.D, pr.DP, pr.bf16, pr.range(), st));
     return FA2_OK;
 }
 
@@ -240,10 +295,11 @@ int run_fwd_main(const Prepared& pr, float* O, float* LSE, cudaStream_t st, cons
     if ((rc = make_tmap_f32(&p.tm_o, O, pr.BH, pr.S, pr.D))) return rc;
     p.O = O; p.LSE = LSE; p.BH = pr.BH; p.S = pr.S; p.D = pr.D;
     p.scale = pr.scale; p.scale_log2 = pr.scale_log2; p.bf16 = pr.bf16;
+    p.range = pr.range()->sc;
     p.timeline = g_timeline;
     if (dO && dQ && mask) {
         p.dO = dO;
-        if (mask & 1) { p.dOh = pr.work + pr.wl.off_do; p.dQ_zero = dQ; }
+        if (mask & 1) { p.dOh = pr.work + pr.wl.off_do; p.dQ_zero = dQ; p.rb = pr.range(); }
         if (mask & 2) {
         p.delta = reinterpret_cast<float*>(pr.work + pr.wl.off_delta);
         p.lse_log2 = reinterpret_cast<float*>(pr.work + pr.wl.off_lse2);
@@ -260,7 +316,7 @@ int run_bwd_prepass(const Prepared& pr, const float* O, const float* dO, const f
     float* lse2 = reinterpret_cast<float*>(pr.work + pr.wl.off_lse2);
     ProfScope prof(2, st);
     FA2_CUDA(launch_bwd_prepass(O, dO, LSE, pr.work + pr.wl.off_do, delta, lse2, dQ, pr.rows, pr.D, pr.DP, pr.bf16,
-                                parts, st));
+                                parts, pr.range(), pr.scale, st));
     return FA2_OK;
 }
 
@@ -278,6 +334,7 @@ int run_bwd_main(const Prepared& pr, float* dQ, float* dK, float* dV, cudaStream
     if ((rc = make_tmap_f32(&p.tm_dv, dV, pr.BH, pr.S, pr.D))) return rc;
     p.lse_log2 = lse2; p.delta = delta; p.dQ = dQ; p.dK = dK; p.dV = dV;
     p.BH = pr.BH; p.S = pr.S; p.D = pr.D; p.scale = pr.scale; p.scale_log2 = pr.scale_log2; p.bf16 = pr.bf16;
+    p.range = pr.range()->sc;
     p.timeline = getenv("FA2_TL_FWD_ONLY") ? nullptr : g_timeline;     // (timeline builds: both kernels share the buffer)
     ProfScope prof(3, st);
     FA2_CUDA(launch_bwd(p, st));
@@ -348,42 +405,32 @@ struct PipeSet {
 };
 PipeSet g_pipes[kMaxDevices];
 
-// Chunk sizes (in slabs) of one device's share.  PCIe is full duplex (measured 2 x 47 GB/s against 55 GB/s one way),
-// so the job takes (bytes one way) / 47 GB/s plus whatever time only one direction is busy: the H2D of the first
-// chunk and, at the end, the D2H of whatever is still on the device when the last H2D finishes -- hence ~32 chunks.
-// The kernels are persistent (one CTA per SM, work items round-robin), so a chunk costs ceil(items / SMs) rounds of
-// one item each whatever its size: the chunk size is picked so that both passes fill their last round (>= 95 % of
-// the SM slots when a size in reach does), otherwise the sum of the per-chunk kernel spans -- what the CLI prints as
-// "Kernel execution completed" (src/main.cpp:107) -- is inflated by idle SMs.
-std::vector<int> plan_chunks(int count, int S, bool fwd, bool bwd, int n_sm = 148) {
+// Chunk sizes (in slabs) of one device's share.  The host path is PCIe-bound (pinned Gen5 x16: ~45 GB/s each way
+// in duplex; the kernels of a chunk take a fraction of its transfer time), so the job takes (bytes of the busier
+// direction) / 45 GB/s plus whatever time only one direction is busy: the H2D of the first chunk and, at the end, the
+// kernels and the D2H of the last one.  Hence chunks as small as the fixed costs allow (~0.5 ms of transfer), grown
+// only until the persistent kernels (a chunk costs ceil(items / SMs) rounds of one work item each, however few SMs
+// its last round fills) keep up with the copies.
+std::vector<int> plan_chunks(int count, int S, int D, bool fwd, bool bwd, int n_sm = 148) {
     std::vector<int> sizes;
     if (count <= 0) return sizes;
-    const int items_f = (S + 255) / 256, items_b = (S + 127) / 128;     // work items per slab (forward / backward kernel)
-    auto eff = [&](int c) {
-        double e = 1.0;
-        for (int pass = 0; pass < 2; ++pass) {
-            if (pass == 0 ? !fwd : !bwd) continue;
-            const long long items = static_cast<long long>(c) * (pass == 0 ? items_f : items_b);
-            const long long slots = (items + n_sm - 1) / n_sm * n_sm;
-            const double x = static_cast<double>(items) / static_cast<double>(slots);
-            if (x < e) e = x;
-        }
-        return e;
+    const double slab_bytes = static_cast<double>(S) * D * 4.0;
+    const double in_b = slab_bytes * (3 + (bwd ? 1 : 0) + (!fwd ? 1 : 0)), out_b = slab_bytes * ((fwd ? 1 : 0) + (bwd ? 3 : 0));
+    const double t_x = (in_b > out_b ? in_b : out_b) / 45e9;                      // seconds of PCIe per slab
+    const int items_f = (S + 255) / 256, items_b = (S + 127) / 128, n_steps = (S + 127) / 128;
+    const double step_f = D > 64 ? 1.65e-6 : 0.95e-6, step_b = D > 64 ? 2.15e-6 : 1.25e-6;   // measured per 128x128 tile step
+    auto kernels = [&](int c) {
+        double t = 10e-6 + c * in_b * 1.5 / 6.5e12;                               // launches + the fp32 -> 16-bit pre-passes
+        if (fwd) t += static_cast<double>((static_cast<long long>(c) * items_f + n_sm - 1) / n_sm) * n_steps * step_f;
+        if (bwd) t += static_cast<double>((static_cast<long long>(c) * items_b + n_sm - 1) / n_sm) * n_steps * step_b;
+        return t;
     };
-    int lo = (count + 31) / 32;
-    const int min_bh = (n_sm + items_b - 1) / items_b;                 // never so small that a chunk cannot fill the SMs
-    if (lo < min_bh) lo = min_bh;
-    if (lo > count) lo = count;
-    int hi = 2 * lo + 8;
-    if (hi > count) hi = count;
-    int best = lo;
-    double best_e = eff(lo);
-    for (int c = lo; c <= hi && best_e < 0.95; ++c) {
-        const double e = eff(c);
-        if (e >= 0.95 || e > best_e + 1e-9) { best = c; best_e = e; }
-    }
+    int c = static_cast<int>(0.5e-3 / t_x + 0.999);
+    if (c < 1) c = 1;
+    if (c > count) c = count;
+    while (c < count && kernels(c) > 0.8 * t_x * c) ++c;
     int left = count;
-    while (left > 0) { const int c = left < best ? left : best; sizes.push_back(c); left -= c; }
+    while (left > 0) { const int n = left < c ? left : c; sizes.push_back(n); left -= n; }
     return sizes;
 }
 
@@ -404,7 +451,7 @@ int host_worker(const HostJob& job, int dev, int bh0, int count, float* ms_out, 
         FA2_CUDA(cudaSetDevice(dev));
         const size_t slab = static_cast<size_t>(job.S) * job.D;           // floats per (b,h)
         const bool fwd = job.mode != FA2_MODE_BACKWARD, bwd = job.mode != FA2_MODE_FORWARD;
-        std::vector<int> sizes = plan_chunks(count, job.S, fwd, bwd);
+        std::vector<int> sizes = plan_chunks(count, job.S, job.D, fwd, bwd);
         int chunk_bh = 0;
         for (int c : sizes) chunk_bh = c > chunk_bh ? c : chunk_bh;
         const int n_chunks = static_cast<int>(sizes.size());
@@ -578,7 +625,7 @@ const char* fa2_last_error(void) { return g_last_error.c_str(); }
 
 size_t fa2_workspace_bytes(int B, int H, int S, int D, int mode) {
     if (B <= 0 || H <= 0 || S <= 0 || (D != 32 && D != 64 && D != 128)) return 0;
-    return work_layout(static_cast<size_t>(B) * H * S, padded_head_dim(D), mode != FA2_MODE_FORWARD).total;
+    return work_layout(static_cast<size_t>(B) * H * S, padded_head_dim(D), mode != FA2_MODE_FORWARD).total;   // incl. the 1 KB range block
 }
 
 int fa2_partition(int BH, int n_parts, int part, int* bh0, int* count) {
@@ -591,10 +638,10 @@ int fa2_partition(int BH, int n_parts, int part, int* bh0, int* count) {
     return FA2_OK;
 }
 
-int fa2_plan_chunks(int count, int S, int mode, int* sizes, int max_chunks) {
-    if (count < 0 || S <= 0 || mode < FA2_MODE_FORWARD || mode > FA2_MODE_FORWARD_BACKWARD || (!sizes && max_chunks > 0))
+int fa2_plan_chunks(int count, int S, int D, int mode, int* sizes, int max_chunks) {
+    if (count < 0 || S <= 0 || D <= 0 || mode < FA2_MODE_FORWARD || mode > FA2_MODE_FORWARD_BACKWARD || (!sizes && max_chunks > 0))
         return -1;
-    const std::vector<int> v = plan_chunks(count, S, mode != FA2_MODE_BACKWARD, mode != FA2_MODE_FORWARD);
+    const std::vector<int> v = plan_chunks(count, S, D, mode != FA2_MODE_BACKWARD, mode != FA2_MODE_FORWARD);
     for (size_t i = 0; i < v.size() && static_cast<int>(i) < max_chunks; ++i) sizes[i] = v[i];
     return static_cast<int>(v.size());
 }
@@ -701,7 +748,7 @@ int fa2_forward(const float* Q, const float* K, const float* V, float* O, float*
     int rc = prepare(&pr, B, H, S, D, precision, false);
     if (rc) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-    if ((rc = run_cast(pr, Q, K, V, st))) return rc;
+    if ((rc = is_small(pr) ? run_cast_small(pr, Q, K, V, nullptr, nullptr, st) : run_cast(pr, Q, K, V, st))) return rc;
     return run_fwd_main(pr, O, LSE, st);
 }
 
@@ -714,8 +761,14 @@ int fa2_backward(const float* Q, const float* K, const float* V, const float* O,
     int rc = prepare(&pr, B, H, S, D, precision, true);
     if (rc) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    if (is_small(pr)) {
+        if ((rc = run_cast_small(pr, Q, K, V, dO, dQ, st))) return rc;          // incl. dO cast, dQ = 0, all scales
+        if ((rc = run_bwd_prepass(pr, O, dO, LSE, dQ, 2, st))) return rc;       // D_i, LSE * log2(e)
+        return run_bwd_main(pr, dQ, dK, dV, st);
+    }
     if ((rc = run_cast(pr, Q, K, V, st))) return rc;
     if ((rc = run_bwd_prepass(pr, O, dO, LSE, dQ, 3, st))) return rc;
+    if ((rc = run_fix_do(pr, dO, st))) return rc;
     return run_bwd_main(pr, dQ, dK, dV, st);
 }
 
@@ -731,6 +784,16 @@ int fa2_forward_backward(const float* Q, const float* K, const float* V, const f
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     // The backward's pre-pass is folded into the forward kernel here: its register-donor warps cast dO and
     // zero-fill dQ in the shadow of the tensor-core loop, its epilogue forms D_i and LSE*log2(e).
+    if (is_small(pr)) {
+        // one cooperative launch prepares everything that does not depend on the forward; the forward's epilogue
+        // still forms D_i and LSE * log2(e) (unless dO is only 16-byte aligned, see below)
+        int mask = fuse_mask() & 2;
+        if (reinterpret_cast<uintptr_t>(dO) & 31u) mask = 0;
+        if ((rc = run_cast_small(pr, Q, K, V, dO, dQ, st))) return rc;
+        if ((rc = run_fwd_main(pr, O, LSE, st, dO, dQ, mask))) return rc;
+        if (!mask && (rc = run_bwd_prepass(pr, O, dO, LSE, dQ, 2, st))) return rc;
+        return run_bwd_main(pr, dQ, dK, dV, st);
+    }
     if ((rc = run_cast(pr, Q, K, V, st))) return rc;           // one 16-bit copy serves both passes
     {
         int mask = fuse_mask();
@@ -740,6 +803,7 @@ int fa2_forward_backward(const float* Q, const float* K, const float* V, const f
         if ((rc = run_fwd_main(pr, O, LSE, st, dO, dQ, mask))) return rc;  // mask != 0: also prepares dO(16 bit) / D_i, LSE*log2e / dQ = 0
         if (mask != 3 && (rc = run_bwd_prepass(pr, O, dO, LSE, dQ, 3 & ~mask, st))) return rc;
     }
+    if ((rc = run_fix_do(pr, dO, st))) return rc;
     return run_bwd_main(pr, dQ, dK, dV, st);
 }
 

@@ -175,13 +175,14 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
             // that their global-memory latency is not on the Q(i) -> S(i) critical path; rows past S: +inf / 0
             // => P = 0, dS = 0
             float r_lse[BT / 32], r_dl[BT / 32];
+            const float delta_mul = p.range != nullptr ? ldg_scalar_volatile(p.range + kDeltaMul) : 1.0f;   // D_i -> units of dP' = dP s_v s_do
 #pragma unroll
             for (int r = 0; r < BT / 32; ++r) {
                 const int row = q_row_of(i) + r * 32 + lane;
                 const bool ok = row < p.S;
                 const size_t g = static_cast<size_t>(bh) * p.S + (ok ? row : 0);
                 r_lse[r] = ok ? __ldg(p.lse_log2 + g) : INFINITY;
-                r_dl[r] = ok ? __ldg(p.delta + g) : 0.0f;
+                r_dl[r] = ok ? __ldg(p.delta + g) * delta_mul : 0.0f;
             }
             mbar_wait(&q_empty[s], ph ^ 1);
             if (elect_one()) {
@@ -331,7 +332,8 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
         const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
         const uint32_t tS = tmem_base + lane_addr + COL_S + h * 64;
         const uint32_t tDP = tmem_base + lane_addr + COL_DP + h * 64;
-        const float2 c2v = make_float2(p.scale_log2, p.scale_log2);
+        const float c2 = p.range != nullptr ? __ldg(p.range + kC2) : p.scale_log2;
+        const float2 c2v = make_float2(c2, c2);
         uint8_t* ds_atom = smem + L::OFF_DS + h * ATOM;        // Q columns [64h, 64h+64) = swizzle atom h
         const bool issuer = ((warp & 3) == 0) && lane == 0;    // owns this warpgroup's dK / dV store groups
         const uint32_t ep_bar = 5 + 2 * h;                      // named barriers private to this warpgroup
@@ -413,8 +415,8 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
                 if (issuer) tma_store_wait_read<0>();
                 named_bar_sync(ep_bar, 128);
             }
-            // dS^T = P^T o (dP^T - D_i): the difference in fp32, the product in packed 16-bit (it is rounded
-            // to 16 bit for the tensor core anyway)
+            // dS^T = P^T o (dP^T - D_i): the difference in fp32 (the staged D_i already carries the operand scales of
+            // dP^T), the product in packed 16-bit (it is rounded to 16 bit for the tensor core anyway)
 #pragma unroll
             for (int sub = 0; sub < 2; ++sub) {
 #pragma unroll
@@ -453,7 +455,8 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
         mbar_wait(dkdv_full, it & 1);
         tc_fence_after();
         if (threadIdx.x == 0) TLC(2);
-        const float mul = (h == 0) ? p.scale : 1.0f;
+        const float mul = (h == 0) ? (p.range != nullptr ? __ldg(p.range + kDkMul) : p.scale)
+                                   : (p.range != nullptr ? __ldg(p.range + kDvMul) : 1.0f);
         const uint32_t tsrc = tmem_base + lane_addr + (h == 0 ? COL_DK : COL_DV);
         const CUtensorMap* tm_out = (h == 0) ? &p.tm_dk : &p.tm_dv;
 #pragma unroll
@@ -506,15 +509,16 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
         const int bh = w / n_tiles, kv_tile = w % n_tiles;
         auto q_row_of = [&](int i) { return q_row_at(kv_tile, i); };
         auto put_chunk = [&](const uint32_t (&rc)[32], int chunk, int i) {
+            const float dq_mul = p.range != nullptr ? ldg_scalar_volatile(p.range + kDqMul) : p.scale;   // 1 / sqrt(D), inverse scales
             if (issuer) tma_store_wait_read<0>();               // previous reduce out of the buffer has been read
             named_bar_sync(bar_id, 128);
 #pragma unroll
             for (int q4 = 0; q4 < 8; ++q4) {
                 float4 v4;
-                v4.x = __uint_as_float(rc[q4 * 4]) * p.scale;
-                v4.y = __uint_as_float(rc[q4 * 4 + 1]) * p.scale;
-                v4.z = __uint_as_float(rc[q4 * 4 + 2]) * p.scale;
-                v4.w = __uint_as_float(rc[q4 * 4 + 3]) * p.scale;
+                v4.x = __uint_as_float(rc[q4 * 4]) * dq_mul;
+                v4.y = __uint_as_float(rc[q4 * 4 + 1]) * dq_mul;
+                v4.z = __uint_as_float(rc[q4 * 4 + 2]) * dq_mul;
+                v4.w = __uint_as_float(rc[q4 * 4 + 3]) * dq_mul;
                 *reinterpret_cast<float4*>(stage + swz128(n, q4)) = v4;
             }
             fence_proxy_async_smem();

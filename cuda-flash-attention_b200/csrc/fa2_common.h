@@ -14,6 +14,32 @@ enum Precision { kOperandF16 = 0, kOperandBF16 = 1 };
 // [BH][S][DP] row-major, DP = padded head dim (64 or 128), zero padded when D < DP.
 inline int padded_head_dim(int D) { return D <= 64 ? 64 : 128; }
 
+// Range block at offset 0 of every per-device workspace: running |x| maxima collected by the cast passes and the
+// per-launch scale factors the fix-up kernels derive from them (the `fp32` API must keep fp32 RANGE although the
+// tensor cores see fp16 operands: a tensor whose largest magnitude does not fit fp16 comfortably is re-cast with a
+// power-of-two scale whose inverse is folded into the softmax scale / the epilogues; exact, since powers of two).
+// The last block of a cast pass turns the maxima into scales and clears them again for the next call.
+constexpr int kAmaxLanes = 16;              // atomics to one address serialise in L2: spread each tensor over 16 words
+enum RangeIdx {
+    kSq = 0, kSk, kSv, kSdo,                // scales applied to the 16-bit copies of Q, K, V, dO (s_do includes the factor
+                                            // that keeps the 16-bit dP - D_i in range)
+    kC2,                                    // log2(e) / sqrt(D) / (s_q s_k)     softmax exponent scale
+    kScaleLse,                              // 1 / sqrt(D) / (s_q s_k)           raw score -> natural-log units
+    kInvV,                                  // 1 / s_v                           folded into O's 1 / l
+    kAmaxV,                                 // max |V| s_v (kept for the dO fix-up)
+    kDeltaMul,                              // s_v s_do                          D_i -> units of dP' = V' dO'^T
+    kDkMul, kDqMul, kDvMul,                 // epilogue factors of dK, dQ, dV (1 / sqrt(D) and the inverse scales)
+    kRangeCount = 16
+};
+struct RangeBlock {
+    unsigned amax[4][kAmaxLanes];           // [Q, K, V, dO][lane]: float bits of max |x| (order-preserving), zero between calls
+    float sc[kRangeCount];
+    unsigned ticket[2];                     // arrivals of the Q/K/V cast blocks / of the dO cast blocks (or donor warps)
+    unsigned coop_arrive, coop_release;     // grid barrier of the small-problem cast kernel (cooperative launch)
+};
+constexpr size_t kRangeBytes = 1024;        // the block's share of the workspace (keeps the tensors 1024-B aligned)
+static_assert(sizeof(RangeBlock) <= kRangeBytes, "RangeBlock must fit its slot");
+
 struct FwdParams {
     CUtensorMap tm_q;   // 16-bit [BH][S][DP], box {64, 128, 1}, 128B swizzle
     CUtensorMap tm_k;
@@ -25,6 +51,8 @@ struct FwdParams {
     float scale_log2;   // log2(e) / sqrt(D)
     float scale;        // 1 / sqrt(D)
     int bf16;
+    const float* range; // RangeBlock::sc of this launch (null: the unscaled defaults above)
+    RangeBlock* rb;     // fused call: the donor warps publish max|dO| and the last of them decides dO's scale
     // fused forward+backward only (all null otherwise): the forward also prepares the backward's side inputs
     const float* dO;    // fp32 [BH][S][D]
     void* dOh;          // 16-bit [BH][S][DP] copy of dO        (register-donor warps)
@@ -51,6 +79,7 @@ struct BwdParams {
     float scale_log2;
     float scale;
     int bf16;
+    const float* range;             // RangeBlock::sc of this launch (null: the unscaled defaults above)
     unsigned long long* timeline;   // debug builds (-DFA2_TIMELINE) only: per-role clock64 stamps of CTA 0
 };
 
@@ -77,12 +106,33 @@ inline cudaError_t ensure_smem_optin(const void* kern, int smem_bytes) {
     return cudaSuccess;
 }
 
+// SM count of the current device (cached per device).
+inline int sm_count_current() {
+    static int count[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (count[dev] == 0 && cudaDeviceGetAttribute(&count[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 148;
+    return count[dev];
+}
+
 // launchers (each returns a cudaError_t from the launch)
 cudaError_t launch_cast_qkv(const float* Q, const float* K, const float* V, void* Qh, void* Kh, void* Vh,
-                            size_t rows, int D, int DP, int bf16, cudaStream_t st);
+                            size_t rows, int D, int DP, int bf16, RangeBlock* rb, float scale,
+                            float scale_log2, cudaStream_t st);
 cudaError_t launch_bwd_prepass(const float* O, const float* dO, const float* LSE, void* dOh, float* delta,
                                float* lse_log2, float* dQ_zero, size_t rows, int D, int DP, int bf16,
-                               int parts /* 1: dO cast + dQ zero, 2: D_i + LSE, 3: both */, cudaStream_t st);
+                               int parts /* 1: dO cast + dQ zero, 2: D_i + LSE, 3: both */, RangeBlock* rb,
+                               float scale, cudaStream_t st);
+// Small problems: ONE cooperative launch measures max|x| of Q, K, V (and dO), decides the scales behind a grid
+// barrier and casts with them (second read served by L2); with dO it also zero-fills dQ.  No re-cast kernels needed.
+cudaError_t launch_cast_small(const float* Q, const float* K, const float* V, const float* dO, void* Qh, void* Kh,
+                              void* Vh, void* dOh, float* dQ_zero, size_t rows, int D, int DP, int bf16, RangeBlock* rb,
+                              float scale, float scale_log2, int n_sm, cudaStream_t st);
+// Re-cast kernels (always launched; they return after one load unless a scale other than 1 was decided).
+cudaError_t launch_range_fix_qkv(const float* Q, const float* K, const float* V, void* Qh, void* Kh, void* Vh,
+                                 size_t rows, int D, int DP, int bf16, const RangeBlock* rb, cudaStream_t st);
+cudaError_t launch_range_fix_do(const float* dO, void* dOh, size_t rows, int D, int DP, int bf16, const RangeBlock* rb,
+                                cudaStream_t st);
 cudaError_t launch_fwd(const FwdParams& p, cudaStream_t st);
 cudaError_t launch_bwd(const BwdParams& p, cudaStream_t st);
 cudaError_t warm_fwd();

@@ -19,6 +19,7 @@
 // meanwhile the MMA warp already computes S(0) of the next item.  Every mbarrier parity is derived
 // from running counters, so the pipeline never drains between items.
 #include "fa2_common.h"
+#include "fa2_range.cuh"
 #include "ptx.cuh"
 
 namespace fa2 {
@@ -280,6 +281,7 @@ fa2_fwd_kernel(const __grid_constant__ FwdParams p) {
             uint4* dOh = static_cast<uint4*>(p.dOh);
             float4* dq = reinterpret_cast<float4*>(p.dQ_zero);
             const bool col_ok = col < p.D;
+            float amax = 0.0f;                                       // max |dO| seen by this thread (range fix-up input)
             for (size_t base = wid * (RPW * U); base < rows; base += nw * (RPW * U)) {
                 float4 a[U], b[U];
 #pragma unroll
@@ -296,6 +298,8 @@ fa2_fwd_kernel(const __grid_constant__ FwdParams p) {
                     if (row < rows) {
                         uint4 out = make_uint4(0u, 0u, 0u, 0u);
                         if (col_ok) {
+                            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(a[u].x), fabsf(a[u].y)), fmaxf(fabsf(a[u].z), fabsf(a[u].w))));
+                            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(b[u].x), fabsf(b[u].y)), fmaxf(fabsf(b[u].z), fabsf(b[u].w))));
                             out.x = BF16 ? pack_bf16x2(a[u].x, a[u].y) : pack_half2(a[u].x, a[u].y);
                             out.y = BF16 ? pack_bf16x2(a[u].z, a[u].w) : pack_half2(a[u].z, a[u].w);
                             out.z = BF16 ? pack_bf16x2(b[u].x, b[u].y) : pack_half2(b[u].x, b[u].y);
@@ -308,6 +312,14 @@ fa2_fwd_kernel(const __grid_constant__ FwdParams p) {
                     }
                 }
             }
+            if (p.rb != nullptr) {
+                // publish max|dO|; the last donor warp of the grid to finish decides dO's scale for the backward
+                const unsigned wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(amax));
+                if (lane == 0) {
+                    if (wmax != 0u) atomicMax(&p.rb->amax[3][wid % kAmaxLanes], wmax);
+                    if (range_last_arrival(&p.rb->ticket[1], 2u * gridDim.x)) decide_do(p.rb, p.D, BF16 ? 1 : 0, p.scale);
+                }
+            }
         }
     } else {
         // ------------------------------------------------------------------ softmax + epilogue
@@ -317,7 +329,8 @@ fa2_fwd_kernel(const __grid_constant__ FwdParams p) {
         const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
         const uint32_t t_s = tmem_base + lane_addr + (t == 0 ? COL_S0 : COL_S1);
         const uint32_t t_o = tmem_base + lane_addr + (t == 0 ? COL_O0 : COL_O1);
-        const float c2 = p.scale_log2;
+        // softmax exponent scale log2(e) / sqrt(D), divided by the power-of-two scales of the 16-bit Q / K copies
+        const float c2 = p.range != nullptr ? __ldg(p.range + kC2) : p.scale_log2;
         uint8_t* stage = smem + L::OFF_STAGE + t * L::STAGE_BYTES;    // this warpgroup's 16 KB O staging buffer
         const bool issuer = (warp & 3) == 0 && lane == 0;              // owns the warpgroup's TMA store groups
         const uint32_t bar_id = 1 + 2 * t;
@@ -445,7 +458,8 @@ fa2_fwd_kernel(const __grid_constant__ FwdParams p) {
             mbar_wait(&o_full[t], mine & 1);
             tc_fence_after();
             if (threadIdx.x == 0) TLC(2);
-            const float inv_l = 1.0f / l_run;
+            // 1 / l, times the inverse of V's power-of-two scale
+            const float inv_l = (p.range != nullptr ? __ldg(p.range + kInvV) : 1.0f) / l_run;
 #pragma unroll
             for (int c = 0; c < DP / 32; ++c) {
                 if (c < n_chunk) {
@@ -485,7 +499,7 @@ fa2_fwd_kernel(const __grid_constant__ FwdParams p) {
             }
             if (row_ok) {
                 const size_t g = static_cast<size_t>(bh) * p.S + q_row;
-                const float lse = m_ref * p.scale + logf(l_run);
+                const float lse = m_ref * (p.range != nullptr ? __ldg(p.range + kScaleLse) : p.scale) + logf(l_run);
                 p.LSE[g] = lse;
                 if (FUSED && p.delta != nullptr) {
                     p.delta[g] = dsum * inv_l;

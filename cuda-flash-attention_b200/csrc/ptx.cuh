@@ -74,6 +74,14 @@ __device__ __forceinline__ void ldg256_stream(const float* p, float (&a)[8]) {
                  : "l"(p));
 }
 
+// Per-launch scalar read where it is used (L1-resident after the first touch) instead of being kept in a register
+// across a loop of a register-starved role; volatile so that the compiler does not hoist it back out.
+__device__ __forceinline__ float ldg_scalar_volatile(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
 __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
     uint32_t r;
     asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));

@@ -120,6 +120,7 @@ def forward(Q, K, V, precision: str = "fp32", stream=None, out=None):
     if len(Q.shape) != 4:
         raise ValueError("Q must be [B,H,S,D]")
     B, H, S, D = Q.shape
+    _check_dev(Q.shape, Q=Q, K=K, V=V)
     O, LSE = out if out is not None else (_empty_like(Q), _empty_like(Q, (B, H, S)))
     dev = _check_dev(Q.shape, Q=Q, K=K, V=V, O=O, LSE=LSE)
     with _on_device(Q, dev):
@@ -133,6 +134,7 @@ def backward(Q, K, V, O, dO, LSE, precision: str = "fp32", stream=None, out=None
     if len(Q.shape) != 4:
         raise ValueError("Q must be [B,H,S,D]")
     B, H, S, D = Q.shape
+    _check_dev(Q.shape, Q=Q, K=K, V=V, O=O, dO=dO, LSE=LSE)
     dQ, dK, dV = out if out is not None else (_empty_like(Q), _empty_like(Q), _empty_like(Q))
     dev = _check_dev(Q.shape, Q=Q, K=K, V=V, O=O, dO=dO, LSE=LSE, dQ=dQ, dK=dK, dV=dV)
     with _on_device(Q, dev):
@@ -146,6 +148,7 @@ def forward_backward(Q, K, V, dO, precision: str = "fp32", stream=None, out=None
     if len(Q.shape) != 4:
         raise ValueError("Q must be [B,H,S,D]")
     B, H, S, D = Q.shape
+    _check_dev(Q.shape, Q=Q, K=K, V=V, dO=dO)
     if out is None:
         out = (_empty_like(Q), _empty_like(Q, (B, H, S)), _empty_like(Q), _empty_like(Q), _empty_like(Q))
     O, LSE, dQ, dK, dV = out

@@ -95,9 +95,10 @@ int fa2_partition(int BH, int n_parts, int part, int* bh0, int* count);
 
 /* The host pipeline's chunking of one device's share of `count` slabs (mode = FA2_MODE_*): writes up to
  * max_chunks chunk sizes (in slabs, in processing order) and returns the number of chunks (-1 on bad
- * arguments).  Chunk sizes are chosen so that the persistent kernels' last round of work items is full.
+ * arguments).  Chunks are as small as the fixed per-chunk costs allow (the path is PCIe-bound, small chunks
+ * shorten the one-directional head and tail) but large enough for the kernels to keep up with the copies.
  * Pure arithmetic, no GPU needed. */
-int fa2_plan_chunks(int count, int S, int mode, int* sizes, int max_chunks);
+int fa2_plan_chunks(int count, int S, int D, int mode, int* sizes, int max_chunks);
 
 /* Number of CUDA devices visible to the library (0 without a GPU; never fails). */
 int fa2_device_count(void);
