@@ -6,9 +6,15 @@ Same command line (`--mode/--kernel/--experiment/--seqlen-experiment/--tolerance
 :177-195), same PyTorch CPU oracle (matmul -> /sqrt(D) -> softmax -> matmul, autograd with dO = ones,
 :197-232), same pass criterion (max-abs error < tolerance and no NaN/Inf, :718-750), same timing
 (1 warm-up + 10 timed launches between CUDA events, :283-308) and the same CSV schema (:1108-1123).
-Differences: kernels are called through the C ABI instead of CuPy NVRTC (CuPy is not in this image); only the
-fa2 kernel exists here (fa1 / vanilla-attn / fa2-naive are comparison baselines of the reference); plots are
+Differences: kernels are called through the C ABI instead of CuPy NVRTC (CuPy is not in this image); plots are
 skipped when matplotlib is unavailable; `--extra-configs` adds the BASELINE.json shapes (D=128, S up to 16384).
+Comparison rows, as in the reference's CSVs (plots/experiment_results.csv: NAIVE, PYTORCH CPU, PYTORCH GPU,
+NAIVE-ATTN, FA2 per configuration): "PyTorch CPU" and "PyTorch GPU" rows are always written; with `--experiment`
+(or `--kernel fa1|vanilla-attn`) and the reference CLI compiled as it lies (oracle/build_ref.sh ->
+oracle/_ref/FlashAttention_ref, or $FA2_BASELINE_CLI) its own CUDA-core kernels are run on the same data through its
+file interface and reported as FA2-REFERENCE / FA1 / NAIVE-ATTN rows (D <= 64: its dispatcher refuses more,
+include/dispatcher.h:226-227).  Those are reported baselines only: nothing of them is linked into libfa2_b200, and
+the fa2-naive kernel (reachable only through the reference's CuPy path, test_flash_attention2.py:315-475) is not run.
 """
 from __future__ import annotations
 
@@ -16,6 +22,10 @@ import argparse
 import csv
 import dataclasses
 import os
+import re
+import shutil
+import subprocess
+import tempfile
 import time
 from dataclasses import dataclass
 from typing import List, Optional
@@ -77,15 +87,30 @@ def create_extra_configs(mode) -> List[TestConfig]:
             TestConfig("Baseline-D-slab", 1, 2, 16384, 128, tb, both), TestConfig("D32", 2, 4, 512, 32, tb, both)]
 
 
+def baseline_cli() -> Optional[str]:
+    """Path of the reference's own CLI built for this GPU (reported baselines only), or None."""
+    cand = [os.environ.get("FA2_BASELINE_CLI", ""),
+            os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "oracle", "_ref",
+                         "FlashAttention_ref")]
+    for c in cand:
+        if c and os.path.isfile(c) and os.access(c, os.X_OK):
+            return c
+    return None
+
+
+BASELINE_METHODS = {"fa2": "FA2-REFERENCE", "fa1": "FA1", "naive": "NAIVE-ATTN"}     # CLI method token -> CSV label
+
+
 class FlashAttention2Tester:
     def __init__(self, stop_on_failure=True, tolerance=1e-3, test_mode="forward", save_results=False,
-                 output_dir="./experiment_results", use_gpu_reference=True, precision="fp32"):
+                 output_dir="./experiment_results", use_gpu_reference=True, precision="fp32", baseline_methods=()):
         import torch
         if not torch.cuda.is_available():
             raise RuntimeError("a CUDA device is required: the FA2 path has no CPU fallback")
         self.stop_on_failure, self.tolerance, self.test_mode = stop_on_failure, tolerance, test_mode
         self.save_results, self.output_dir, self.use_gpu_reference = save_results, output_dir, use_gpu_reference
         self.precision = precision
+        self.baseline_methods = tuple(baseline_methods) if baseline_cli() else ()
         self.results: List[TestResult] = []
         if save_results:
             os.makedirs(output_dir, exist_ok=True)
@@ -152,6 +177,79 @@ class FlashAttention2Tester:
         ms = self._timed(lambda: api.backward(q, k, v, o, g, l, precision=self.precision, out=out))
         return {n: t.cpu().numpy() for n, t in zip(("dQ", "dK", "dV"), out)}, ms
 
+    # ---- reported baselines: the reference's own kernels through its CLI (file in, file out) ----------------
+    def run_reference_cli(self, method: str, mode: str, Q, K, V):
+        """Runs `<reference CLI> <method> <mode> fp32 <dir>` on these tensors (dO = ones: no dO.bin, src/main.cpp:83-93)
+        and returns ({name: array}, kernel_ms) with its own TimerGPU figure ("Kernel execution completed", :107)."""
+        exe = baseline_cli()
+        B, H, S, D = Q.shape
+        tmp = tempfile.mkdtemp(prefix="fa2_baseline_")
+        try:
+            d = os.path.join(tmp, f"B{B}_H{H}_S{S}_D{D}")
+            os.makedirs(d)
+            for n, t in zip("QKV", (Q, K, V)):
+                t.detach().cpu().numpy().astype(np.float32).tofile(os.path.join(d, f"{n}.bin"))
+            r = subprocess.run([exe, method, mode, "fp32", d], capture_output=True, text=True, timeout=600)
+            if r.returncode != 0:
+                raise RuntimeError((r.stderr or r.stdout).strip().splitlines()[-1] if (r.stderr or r.stdout).strip() else "failed")
+            m = re.search(r"Kernel execution completed:\s*([0-9.eE+-]+)\s*seconds", r.stdout)
+            ms = float(m.group(1)) * 1e3 if m else float("nan")
+            out = {}
+            for n, shp in (("O", (B, H, S, D)), ("dQ", (B, H, S, D)), ("dK", (B, H, S, D)), ("dV", (B, H, S, D))):
+                f = os.path.join(d, n + ".bin")
+                if os.path.exists(f):
+                    out[n] = np.fromfile(f, np.float32).reshape(shp)
+            return out, ms
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+
+    def baseline_rows(self, config, Q, K, V, expected, exp_g, torch_fwd_ms, torch_bwd_ms):
+        rows = []
+        if config.head_dim > 64:
+            return rows
+        cat = lambda d: np.concatenate([np.asarray(d[n]).ravel() for n in ("dQ", "dK", "dV")])
+        for method in self.baseline_methods:
+            label = BASELINE_METHODS[method]
+            cfg = dataclasses.replace(config, kernel_type=label)
+            try:
+                if self.test_mode == "forward":
+                    out, ms = self.run_reference_cli(method, "forward", Q, K, V)
+                    rows.append(self._result(cfg, "forward", out["O"], expected.numpy(), ms, torch_fwd_ms, 1.0))
+                elif method == "fa2":               # the reference has a backward for fa2 only (dispatcher.h:74-83)
+                    out, ms = self.run_reference_cli(method, "forward_backward", Q, K, V)
+                    rows.append(self._result(cfg, "both", cat(out), exp_g, ms, torch_fwd_ms + torch_bwd_ms, 3.5))
+            except Exception as ex:               # a baseline that cannot run is reported, never fatal
+                rows.append(TestResult(cfg, False, float("nan"), float("nan"), float("nan"), float("nan"), 0.0, 0.0, 0.0,
+                                       0.0, 0.0, self.test_mode, f"baseline unavailable: {ex}"))
+        return rows
+
+    def pytorch_gpu_backward_row(self, config, Q, K, V, exp_g, torch_ms):
+        """PyTorch GPU (SDPA, math backend) forward + autograd backward with dO = ones (reference :651-706)."""
+        import torch
+        import torch.nn.functional as F
+        from torch.nn.attention import SDPBackend, sdpa_kernel
+        q, k, v = (t.detach().cuda().requires_grad_(True) for t in (Q, K, V))
+
+        def run():
+            for t in (q, k, v):
+                t.grad = None
+            with sdpa_kernel(SDPBackend.MATH):
+                o = F.scaled_dot_product_attention(q, k, v)
+            o.backward(torch.ones_like(o))
+        ms = self._timed(run, num_runs=5)
+        got = np.concatenate([t.grad.cpu().numpy().ravel() for t in (q, k, v)])
+        cfg = dataclasses.replace(config, kernel_type="PyTorch GPU")
+        return self._result(cfg, "backward", got, exp_g, ms, torch_ms, 3.5)
+
+    @staticmethod
+    def pytorch_cpu_row(config, test_type, torch_ms, flop_mult):
+        """The reference writes its CPU oracle as a row of its own (errors 0, speedup 1; :635-648)."""
+        flops = 4.0 * config.batch_size * config.num_heads * config.seq_len ** 2 * config.head_dim * flop_mult
+        nbytes = config.batch_size * config.num_heads * config.seq_len * config.head_dim * 4 * 4
+        cfg = dataclasses.replace(config, kernel_type="PyTorch CPU")
+        t = max(torch_ms, 1e-9) * 1e-3
+        return TestResult(cfg, True, 0.0, 0.0, 0.0, 0.0, torch_ms, torch_ms, 1.0, flops / t / 1e12, nbytes / t / 1e9, test_type)
+
     # ---- metrics (reference :569-606) ---------------------------------------------------------------
     @staticmethod
     def compute_metrics(actual, expected, kernel_time, torch_time, config, flop_mult=1.0):
@@ -183,6 +281,8 @@ class FlashAttention2Tester:
         torch_fwd_ms = (time.time() - t0) * 1e3
         out: List[TestResult] = []
         cat = lambda d: np.concatenate([np.asarray(d[n]).ravel() for n in ("dQ", "dK", "dV")])
+        if self.test_mode == "forward":
+            out.append(self.pytorch_cpu_row(config, "forward", torch_fwd_ms, 1.0))
         if self.use_gpu_reference and self.test_mode == "forward":
             import torch.nn.functional as F
             qg, kg, vg = (t.cuda() for t in (Q, K, V))
@@ -193,11 +293,16 @@ class FlashAttention2Tester:
             out.append(self._result(cfg, "forward", F.scaled_dot_product_attention(qg, kg, vg).cpu().numpy(),
                                     expected.numpy(), ms, torch_fwd_ms, 1.0))
         if self.test_mode == "forward":
+            out.extend(self.baseline_rows(config, Q, K, V, expected, None, torch_fwd_ms, 0.0))
             O, _, ms = self.run_fa2_forward_kernel(Q, K, V)
             out.append(self._result(config, "forward", O, expected.numpy(), ms, torch_fwd_ms, 1.0))
             return out
         _, grads, torch_bwd_ms = self.compute_reference_grads(Q, K, V)
         exp_g = cat(dict(zip(("dQ", "dK", "dV"), (g.numpy() for g in grads))))
+        out.append(self.pytorch_cpu_row(config, self.test_mode, torch_fwd_ms + torch_bwd_ms, 3.5))
+        if self.use_gpu_reference:
+            out.append(self.pytorch_gpu_backward_row(config, Q, K, V, exp_g, torch_fwd_ms + torch_bwd_ms))
+        out.extend(self.baseline_rows(config, Q, K, V, expected, exp_g, torch_fwd_ms, torch_bwd_ms))
         if self.test_mode == "backward":           # PyTorch forward feeds the CUDA backward (:917-928)
             g, ms = self.run_cuda_fa2_backward_kernel(Q, K, V, expected.numpy(), self.compute_lse(Q, K).numpy())
             out.append(self._result(config, "backward", cat(g), exp_g, ms, torch_fwd_ms + torch_bwd_ms, 2.5))
@@ -210,9 +315,6 @@ class FlashAttention2Tester:
 
     def run_all_tests(self, configs: List[TestConfig]):
         for cfg in configs:
-            if cfg.kernel_type != "fa2":
-                print(f"skipping {cfg.name}: kernel '{cfg.kernel_type}' is a reference comparison baseline (not provided)")
-                continue
             try:
                 results = self.run_test(cfg)
             except Exception as ex:                          # same behaviour as the reference: record and go on / stop
@@ -222,7 +324,7 @@ class FlashAttention2Tester:
             for r in results:
                 print(f"  {r.config.kernel_type:12s} {r.test_type:8s} {'PASS' if r.passed else 'FAIL'}  max_err={r.max_abs_error:.2e} "
                       f"time={r.kernel_time_ms:.4f} ms  {r.tflops:.1f} TFLOPS  speedup vs CPU {r.speedup:.1f}x")
-            if self.stop_on_failure and not all(r.passed for r in results):
+            if self.stop_on_failure and not all(r.passed for r in results if r.config.kernel_type == "fa2"):
                 print("Stopping on first failure")
                 break
         self.results.sort(key=lambda x: x.config.batch_size * x.config.num_heads * x.config.seq_len * x.config.head_dim)
@@ -271,17 +373,30 @@ def main(argv: Optional[List[str]] = None) -> int:
     ap.add_argument("--no-gpu-reference", action="store_true")
     ap.add_argument("--precision", default="fp32", choices=["fp32", "fp16", "bf16"])
     ap.add_argument("--extra-configs", action="store_true", help="add the BASELINE.json shapes (D=128, long S)")
+    ap.add_argument("--no-baselines", action="store_true", help="do not run the reference's own kernels as comparison rows")
     a = ap.parse_args(argv)
+    baselines = ()
+    if a.kernel == "fa2-naive":
+        ap.error("kernel 'fa2-naive' is reachable only through the reference's CuPy path and is not provided here")
     if a.kernel != "fa2":
-        ap.error(f"kernel '{a.kernel}' is a comparison baseline of the reference and is not provided; only 'fa2' exists here")
+        # the reference's comparison kernels run as reported baselines through its own CLI; fa2 is always the kernel under test
+        if a.mode != "forward":
+            ap.error("Backward pass testing is only supported for the FA2 kernel")        # reference :1494-1495
+        if baseline_cli() is None:
+            ap.error(f"kernel '{a.kernel}' is a comparison baseline of the reference: build its CLI with oracle/build_ref.sh "
+                     "(or point $FA2_BASELINE_CLI at it); only 'fa2' is implemented here")
+        baselines = ({"fa1": "fa1", "vanilla-attn": "naive"}[a.kernel],)
+    elif a.experiment and not a.no_baselines:
+        baselines = ("fa2", "fa1", "naive") if a.mode == "forward" else ("fa2",)
     configs = (create_sequence_length_experiment_configs(a.mode) if a.seqlen_experiment
                else create_test_configs(a.mode, "fa2"))
     if a.extra_configs:
         configs += create_extra_configs(a.mode)
     t = FlashAttention2Tester(not a.no_stop_on_failure, a.tolerance, a.mode, a.save_results, a.output_dir,
-                              not a.no_gpu_reference, a.precision)
+                              not a.no_gpu_reference, a.precision, baselines)
     t.run_all_tests(configs)
-    return 0 if all(r.passed for r in t.results) else 1
+    own = [r for r in t.results if r.config.kernel_type == "fa2"]       # baseline rows are reported, not judged
+    return 0 if own and all(r.passed for r in own) else 1
 
 
 if __name__ == "__main__":

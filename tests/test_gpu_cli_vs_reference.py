@@ -65,6 +65,65 @@ def test_cli_forward_backward_with_dO_file_and_alias(tmp_path):
         assert np.abs(load(d, n, shp) - want).max() < 1e-2, n
 
 
+def test_cli_streamed_chunks_equal_serial_order(tmp_path):
+    """The CLI streams read -> compute -> write in chunks of slabs through three buffer sets; FA2_CLI_STREAM=0 is the
+    reference's load-all / compute / save-all order (src/main.cpp:74-118).  Same files either way (dQ up to the
+    reduce-add order), for all three modes, with and without dO.bin."""
+    B, H, S, D = 2, 12, 512, 64                                  # 24 slabs of 128 KiB: 1 MiB chunks -> 3 chunks
+    a = make_dir(str(tmp_path / "a"), B, H, S, D, with_dO=True)
+    b = os.path.join(str(tmp_path / "b"), os.path.basename(a))
+    shutil.copytree(a, b)
+    env_s = dict(os.environ, FA2_CLI_CHUNK_MB="1")
+    env_n = dict(os.environ, FA2_CLI_STREAM="0")
+    shp = (B, H, S, D)
+    for mode, names in (("forward", ("O", "logsumexp")), ("backward", ("dQ", "dK", "dV")),
+                        ("forward_backward", ("O", "logsumexp", "dQ", "dK", "dV"))):
+        r1 = subprocess.run([CLI, "fa2", mode, "fp32", a], capture_output=True, text=True, timeout=300, env=env_s)
+        r2 = subprocess.run([CLI, "fa2", mode, "fp32", b], capture_output=True, text=True, timeout=300, env=env_n)
+        assert r1.returncode == 0 and r2.returncode == 0, r1.stderr + r2.stderr
+        assert "streamed in 3 chunk(s)" in r1.stdout and "serial load" in r2.stdout
+        for n in names:
+            x = load(a, n, (B, H, S) if n == "logsumexp" else shp)
+            y = load(b, n, (B, H, S) if n == "logsumexp" else shp)
+            if n == "dQ":
+                assert np.abs(x - y).max() < 1e-5
+            else:
+                assert np.array_equal(x, y), (mode, n)
+
+
+def test_cli_hands_baseline_methods_to_the_reference_cli(tmp_path):
+    """fa1 / naive are comparison baselines of the reference (include/dispatcher.h:30-51): with the reference's own CLI
+    available the call is handed over to it, otherwise it is refused with a message."""
+    d = make_dir(str(tmp_path), 1, 2, 128, 64)
+    if os.path.exists(REF):
+        r = subprocess.run([CLI, "fa1", "forward", "fp32", d], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0 and "comparison baseline" in r.stderr and "Kernel execution completed" in r.stdout
+        Q, K, V = (load(d, n, (1, 2, 128, 64)) for n in "QKV")
+        from oracle import fa2_oracle as orc
+        assert np.abs(load(d, "O", (1, 2, 128, 64)) - orc.attention_fp64(Q, K, V)[0]).max() < 1e-4
+    r = subprocess.run([CLI, "naive", "forward", "fp32", d], capture_output=True, text=True, timeout=300,
+                       env=dict(os.environ, FA2_BASELINE_CLI="/nonexistent"))
+    assert r.returncode == 1 and "comparison baseline" in r.stderr
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/FlashAttention_ref not built")
+@pytest.mark.parametrize("B,H,S,D,prec", [(2, 8, 512, 64, "fp32"), (4, 16, 1024, 64, "fp16")])
+def test_baseline_configs_at_full_size_against_the_reference_cli(tmp_path, B, H, S, D, prec):
+    """BASELINE.json configs[0] and configs[1] at their FULL size: ours (with the config's precision flag) against the
+    reference's fp32 fa2 kernels on the same files (its fp16-SHM mode keeps accumulators in half and is only a loose
+    oracle)."""
+    ours = make_dir(str(tmp_path / "ours"), B, H, S, D, with_dO=True)
+    theirs = os.path.join(str(tmp_path / "ref"), os.path.basename(ours))
+    shutil.copytree(ours, theirs)
+    run(REF, "fa2", "forward_backward", "fp32", theirs)
+    run(CLI, "fa2", "forward_backward", prec, ours)
+    shp = (B, H, S, D)
+    for n, tol, s in (("O", 1e-2, shp), ("logsumexp", 1e-3, (B, H, S)), ("dQ", 1e-2, shp), ("dK", 1e-2, shp), ("dV", 1e-2, shp)):
+        a, b = load(ours, n, s), load(theirs, n, s)
+        assert np.isfinite(a).all()
+        assert np.abs(a - b).max() < tol, (n, float(np.abs(a - b).max()))
+
+
 def test_cli_multi_gpu_flag_single_device_ok(tmp_path):
     d = make_dir(str(tmp_path), 1, 4, 128, 64)
     run(CLI, "fa2", "forward", "fp32", d, "--gpus", "1")

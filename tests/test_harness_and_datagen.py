@@ -49,8 +49,10 @@ def test_harness_both_mode_end_to_end(tmp_path):
                        "--no-gpu-reference"])
     rows = list(csv.DictReader(open(tmp_path / "experiment_results.csv")))
     assert rc == 0, [r for r in rows if r["Status"] != "PASS"]
-    assert len(rows) == 20 and set(rows[0]) == set(harness.CSV_COLUMNS)       # 10 configs x (forward, backward)
-    assert all(float(r["MaxError"]) < 1e-3 for r in rows)                    # the reference's own tolerance
+    ours = [r for r in rows if r["Kernel"] == "FA2"]
+    assert len(ours) == 20 and set(rows[0]) == set(harness.CSV_COLUMNS)       # 10 configs x (forward, backward)
+    assert all(float(r["MaxError"]) < 1e-3 for r in ours)                    # the reference's own tolerance
+    assert sum(r["Kernel"] == "PYTORCH CPU" for r in rows) == 10             # the CPU oracle as a row of its own (:635-648)
 
 
 @pytest.mark.gpu
@@ -61,3 +63,29 @@ def test_harness_forward_with_gpu_reference_and_extra_configs(tmp_path):
     ours = [r for r in t.results if r.config.kernel_type == "fa2"]
     assert len(ours) == 4 and all(r.passed for r in ours)
     assert any(r.config.kernel_type == "PyTorch GPU" for r in t.results)
+
+
+@pytest.mark.gpu
+def test_harness_experiment_reports_the_reference_kernels_as_baseline_rows(tmp_path):
+    """--experiment lays our FA2 beside the reference's own CUDA-core kernels (fa2, fa1, vanilla) run through its CLI
+    on the same data, like plots/experiment_results.csv; those rows are reported, only the FA2 rows are judged."""
+    from fa2_b200 import harness
+    if harness.baseline_cli() is None:
+        pytest.skip("oracle/_ref/FlashAttention_ref not built")
+    t = harness.FlashAttention2Tester(stop_on_failure=False, tolerance=1e-3, test_mode="forward", save_results=True,
+                                      output_dir=str(tmp_path), baseline_methods=("fa2", "fa1", "naive"))
+    t.run_all_tests(harness.create_test_configs("forward")[1:4])
+    kinds = {}
+    for r in t.results:
+        kinds.setdefault(r.config.kernel_type, []).append(r)
+    for k in ("fa2", "FA2-REFERENCE", "FA1", "NAIVE-ATTN", "PyTorch CPU", "PyTorch GPU"):
+        assert len(kinds.get(k, [])) == 3, (k, list(kinds))
+    assert all(r.passed for r in kinds["fa2"])
+    assert all(r.passed and r.max_abs_error < 1e-5 for r in kinds["FA2-REFERENCE"])   # fp32 CUDA-core kernels
+    assert all(np.isfinite(r.kernel_time_ms) and r.kernel_time_ms > 0 for r in kinds["FA1"] + kinds["NAIVE-ATTN"])
+    t2 = harness.FlashAttention2Tester(stop_on_failure=False, tolerance=1e-3, test_mode="both", baseline_methods=("fa2",))
+    t2.run_all_tests(harness.create_test_configs("both")[1:2])
+    ref = [r for r in t2.results if r.config.kernel_type == "FA2-REFERENCE"]
+    assert len(ref) == 1 and ref[0].passed and ref[0].test_type == "both"
+    rows = list(csv.DictReader(open(tmp_path / "experiment_results.csv")))
+    assert {"FA2", "FA2-REFERENCE", "FA1", "NAIVE-ATTN", "PYTORCH CPU", "PYTORCH GPU"} <= {r["Kernel"] for r in rows}
