@@ -415,6 +415,39 @@ def main():
         except RuntimeError as ex:
             print("pcie probe failed on rank %d: %s" % (rank, ex), file=sys.stderr)
 
+    # ---- strong scaling, device-resident: ONE workload-sized problem split over the N ranks by fa2_partition; every
+    # rank times its share (B*H / N slabs) with the same events as above, T_N = max over ranks, T_1 = the full
+    # workload on one GPU (the weak-scaling step above is exactly that).  No collective: slabs are independent.
+    strong_dev = None
+    if world > 1 and not args.no_strong:
+        _, share = fa2_b200.partition(B * H, world, rank)
+        if share > 0:
+            sq, sk, sv, sg = (t_.view(1, B * H, S, D)[:, :share] for t_ in (q, k, v, do))
+            souts = tuple(t_.view(1, B * H, *t_.shape[2:])[:, :share] for t_ in outs)
+            sq, sk, sv, sg = (t_.contiguous() for t_ in (sq, sk, sv, sg))
+            souts = tuple(t_.contiguous() for t_ in souts)
+            for _ in range(args.warmup):
+                fa2_b200.forward_backward(sq, sk, sv, sg, precision=prec, out=souts)
+            barrier()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record(st)
+            for _ in range(args.steps):
+                fa2_b200.forward_backward(sq, sk, sv, sg, precision=prec, out=souts)
+            s1.record(st)
+            barrier()
+            tN = all_max(s0.elapsed_time(s1) / args.steps)
+        else:
+            barrier(); barrier()
+            tN = all_max(0.0)
+        items_f, items_b = share * ((S + 255) // 256), share * ((S + 127) // 128)
+        strong_dev = {"problem": f"ONE B{B} H{H} S{S} D{D} problem, {B * H // world} slabs per GPU (fa2_partition), device-resident",
+                      "T1_ms": ms_step, "TN_ms": tN, "efficiency": ms_step / (world * tN) if tN > 0 else None,
+                      "tflops_aggregate": (f_fwd + f_bwd) / (tN * 1e-3) / 1e12 if tN > 0 else None,
+                      "limiter": f"wave quantisation on 148 persistent CTAs: forward {items_f} items = {items_f / 148:.2f} waves "
+                                 f"-> {-(-items_f // 148)} rounds, backward {items_b} items = {items_b / 148:.2f} waves -> "
+                                 f"{-(-items_b // 148)} rounds; predicted efficiency "
+                                 f"{(2 * items_f / 148 + 5 * items_b / 148) / (2 * -(-items_f // 148) + 5 * -(-items_b // 148)):.3f}"}
+
     # ---- strong scaling of the product's partitioner: ONE workload-sized problem over N GPUs (rank 0 drives all of
     # them through fa2_host_forward_backward; the other ranks wait on a host-side barrier with their GPUs idle)
     strong = None
@@ -517,8 +550,8 @@ def main():
                 "ms_per_step": t_e2e * 1e3 if t_e2e != float("inf") else None,
                 "per_gpu": e2e_val / world if e2e_val else None, "kernel_ms_inside": e2e_kernel_ms, "pcie": pcie},
     }
-    if strong is not None:
-        line["strong_scaling"] = strong
+    if strong is not None or strong_dev is not None:
+        line["strong_scaling"] = {"device": strong_dev, "host_api": strong}
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(B, H, S, D)
     print(json.dumps(line))
@@ -526,6 +559,7 @@ def main():
     if dist is not None:
         dist.destroy_process_group()
     bad = (verify is not None and not verify["ok"]) or (strong is not None and not strong.get("equal_to_1gpu", False))
+    strong = {"device": strong_dev, "host_api": strong}
     if bad:
         print("bench.py: OUTPUT CHECK FAILED: " + json.dumps({"verify": verify, "strong": strong}), file=sys.stderr)
         sys.exit(1)

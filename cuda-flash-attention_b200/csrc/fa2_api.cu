@@ -15,6 +15,8 @@
 #include <cstring>
 #include <initializer_list>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -65,8 +67,10 @@ EncodeTiledFn get_encode_fn() {
 // Descriptors are a pure function of (base, geometry, type): a small per-thread cache saves the 4 + 7 driver calls
 // per forward + backward call when the same tensors come back (training loops, the harness's timed repeats).
 struct TmapKey {
-    const void* base; int BH, S, D, kind;      // kind: 0 = fp16 copy, 1 = bf16 copy, 2 = fp32 tensor
-    bool operator==(const TmapKey& o) const { return base == o.base && BH == o.BH && S == o.S && D == o.D && kind == o.kind; }
+    const void* base; int BH, S, pitch, D, kind;      // kind: 0 = fp16 copy, 1 = bf16 copy, 2 = fp32 tensor
+    bool operator==(const TmapKey& o) const {
+        return base == o.base && BH == o.BH && S == o.S && pitch == o.pitch && D == o.D && kind == o.kind;
+    }
 };
 struct TmapCache {
     static constexpr int N = 32;
@@ -84,14 +88,16 @@ struct TmapCache {
 };
 thread_local TmapCache g_tmaps;
 
-// 16-bit [BH][S][DP] tensor, box {64 cols, box_rows, 1 slab}, 128-byte swizzle, zero OOB fill.
-int make_tmap_16(CUtensorMap* tm, void* base, int BH, int S, int DP, int box_rows, int bf16) {
-    const TmapKey k{base, BH, S, DP, bf16 ? 1 : 0};
+// 16-bit [BH][S][DP] tensor, box {64 cols, box_rows, 1 slab}, 128-byte swizzle, zero OOB fill.  pitch_rows > 0: the S
+// rows are a row range of slabs that are pitch_rows apart in memory (base points at the first row of the range).
+int make_tmap_16(CUtensorMap* tm, void* base, int BH, int S, int DP, int box_rows, int bf16, int pitch_rows = 0) {
+    if (pitch_rows <= 0) pitch_rows = S;
+    const TmapKey k{base, BH, S, pitch_rows, DP, bf16 ? 1 : 0};
     if (const CUtensorMap* hit = g_tmaps.find(k)) { *tm = *hit; return FA2_OK; }
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return fail(FA2_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
     cuuint64_t dims[3] = {static_cast<cuuint64_t>(DP), static_cast<cuuint64_t>(S), static_cast<cuuint64_t>(BH)};
-    cuuint64_t strides[2] = {static_cast<cuuint64_t>(DP) * 2, static_cast<cuuint64_t>(S) * DP * 2};
+    cuuint64_t strides[2] = {static_cast<cuuint64_t>(DP) * 2, static_cast<cuuint64_t>(pitch_rows) * DP * 2};
     cuuint32_t box[3] = {64, static_cast<cuuint32_t>(box_rows), 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(tm, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, base, dims,
@@ -103,13 +109,14 @@ int make_tmap_16(CUtensorMap* tm, void* base, int BH, int S, int DP, int box_row
 }
 
 // fp32 [BH][S][D] tensor addressed by the dQ reduce-add: box {32 cols, 128 rows, 1 slab}, 128-byte swizzle.
-int make_tmap_f32(CUtensorMap* tm, void* base, int BH, int S, int D) {
-    const TmapKey k{base, BH, S, D, 2};
+int make_tmap_f32(CUtensorMap* tm, void* base, int BH, int S, int D, int pitch_rows = 0) {
+    if (pitch_rows <= 0) pitch_rows = S;
+    const TmapKey k{base, BH, S, pitch_rows, D, 2};
     if (const CUtensorMap* hit = g_tmaps.find(k)) { *tm = *hit; return FA2_OK; }
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return fail(FA2_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
     cuuint64_t dims[3] = {static_cast<cuuint64_t>(D), static_cast<cuuint64_t>(S), static_cast<cuuint64_t>(BH)};
-    cuuint64_t strides[2] = {static_cast<cuuint64_t>(D) * 4, static_cast<cuuint64_t>(S) * D * 4};
+    cuuint64_t strides[2] = {static_cast<cuuint64_t>(D) * 4, static_cast<cuuint64_t>(pitch_rows) * D * 4};
     cuuint32_t box[3] = {32, 128, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr,
@@ -285,24 +292,30 @@ int fuse_mask() {
 
 // dO / dQ non-null = fused forward+backward: the forward kernel also writes the 16-bit dO copy, D_i, LSE*log2(e)
 // and zero-fills dQ, so no separate backward pre-pass is launched.
+// Row range of every slab a launch covers (sequence-split path); {0, S} = everything.
+struct RowRange { int r0, r1; };
+
 int run_fwd_main(const Prepared& pr, float* O, float* LSE, cudaStream_t st, const float* dO = nullptr,
-                 float* dQ = nullptr, int mask = 0) {
+                 float* dQ = nullptr, int mask = 0, const RowRange* qr = nullptr) {
+    const int r0 = qr ? qr->r0 : 0, Sq = qr ? qr->r1 - qr->r0 : pr.S;
+    const size_t e0 = static_cast<size_t>(r0) * pr.D, h0 = static_cast<size_t>(r0) * pr.DP * 2;
     FwdParams p{};
     int rc;
-    if ((rc = make_tmap_16(&p.tm_q, pr.work + pr.wl.off_q, pr.BH, pr.S, pr.DP, 128, pr.bf16))) return rc;
+    if ((rc = make_tmap_16(&p.tm_q, pr.work + pr.wl.off_q + h0, pr.BH, Sq, pr.DP, 128, pr.bf16, pr.S))) return rc;
     if ((rc = make_tmap_16(&p.tm_k, pr.work + pr.wl.off_k, pr.BH, pr.S, pr.DP, 128, pr.bf16))) return rc;
     if ((rc = make_tmap_16(&p.tm_v, pr.work + pr.wl.off_v, pr.BH, pr.S, pr.DP, 128, pr.bf16))) return rc;
-    if ((rc = make_tmap_f32(&p.tm_o, O, pr.BH, pr.S, pr.D))) return rc;
-    p.O = O; p.LSE = LSE; p.BH = pr.BH; p.S = pr.S; p.D = pr.D;
+    if ((rc = make_tmap_f32(&p.tm_o, O + e0, pr.BH, Sq, pr.D, pr.S))) return rc;
+    p.O = O + e0; p.LSE = LSE + r0; p.BH = pr.BH; p.S_q = Sq; p.S_kv = pr.S; p.q_pitch = pr.S; p.D = pr.D;
+    p.donor_rows = static_cast<long long>(pr.rows);
     p.scale = pr.scale; p.scale_log2 = pr.scale_log2; p.bf16 = pr.bf16;
     p.range = pr.range()->sc;
     p.timeline = g_timeline;
     if (dO && dQ && mask) {
-        p.dO = dO;
+        p.dO = dO + e0;
         if (mask & 1) { p.dOh = pr.work + pr.wl.off_do; p.dQ_zero = dQ; p.rb = pr.range(); }
         if (mask & 2) {
-        p.delta = reinterpret_cast<float*>(pr.work + pr.wl.off_delta);
-        p.lse_log2 = reinterpret_cast<float*>(pr.work + pr.wl.off_lse2);
+            p.delta = reinterpret_cast<float*>(pr.work + pr.wl.off_delta) + r0;
+            p.lse_log2 = reinterpret_cast<float*>(pr.work + pr.wl.off_lse2) + r0;
         }
     }
     ProfScope prof(1, st);
@@ -311,29 +324,34 @@ int run_fwd_main(const Prepared& pr, float* O, float* LSE, cudaStream_t st, cons
 }
 
 int run_bwd_prepass(const Prepared& pr, const float* O, const float* dO, const float* LSE, float* dQ, int parts,
-                    cudaStream_t st) {
-    float* delta = reinterpret_cast<float*>(pr.work + pr.wl.off_delta);
-    float* lse2 = reinterpret_cast<float*>(pr.work + pr.wl.off_lse2);
+                    cudaStream_t st, const RowRange* qr = nullptr) {
+    const int r0 = qr ? qr->r0 : 0, n = qr ? qr->r1 - qr->r0 : pr.S;
+    const size_t e0 = static_cast<size_t>(r0) * pr.D;
+    float* delta = reinterpret_cast<float*>(pr.work + pr.wl.off_delta) + r0;
+    float* lse2 = reinterpret_cast<float*>(pr.work + pr.wl.off_lse2) + r0;
     ProfScope prof(2, st);
-    FA2_CUDA(launch_bwd_prepass(O, dO, LSE, pr.work + pr.wl.off_do, delta, lse2, dQ, pr.rows, pr.D, pr.DP, pr.bf16,
-                                parts, pr.range(), pr.scale, st));
+    FA2_CUDA(launch_bwd_prepass(O + e0, dO + e0, LSE + r0, pr.work + pr.wl.off_do + static_cast<size_t>(r0) * pr.DP * 2, delta,
+                                lse2, dQ + e0, static_cast<size_t>(pr.BH) * n, pr.D, pr.DP, pr.bf16, parts, pr.range(),
+                                pr.scale, st, static_cast<unsigned>(n), static_cast<unsigned>(pr.S)));
     return FA2_OK;
 }
 
-int run_bwd_main(const Prepared& pr, float* dQ, float* dK, float* dV, cudaStream_t st) {
+int run_bwd_main(const Prepared& pr, float* dQ, float* dK, float* dV, cudaStream_t st, const RowRange* kr = nullptr) {
+    const int r0 = kr ? kr->r0 : 0, Skv = kr ? kr->r1 - kr->r0 : pr.S;
+    const size_t e0 = static_cast<size_t>(r0) * pr.D, h0 = static_cast<size_t>(r0) * pr.DP * 2;
     float* delta = reinterpret_cast<float*>(pr.work + pr.wl.off_delta);
     float* lse2 = reinterpret_cast<float*>(pr.work + pr.wl.off_lse2);
     BwdParams p{};
     int rc;
     if ((rc = make_tmap_16(&p.tm_q, pr.work + pr.wl.off_q, pr.BH, pr.S, pr.DP, 128, pr.bf16))) return rc;
-    if ((rc = make_tmap_16(&p.tm_k, pr.work + pr.wl.off_k, pr.BH, pr.S, pr.DP, 128, pr.bf16))) return rc;
-    if ((rc = make_tmap_16(&p.tm_v, pr.work + pr.wl.off_v, pr.BH, pr.S, pr.DP, 128, pr.bf16))) return rc;
+    if ((rc = make_tmap_16(&p.tm_k, pr.work + pr.wl.off_k + h0, pr.BH, Skv, pr.DP, 128, pr.bf16, pr.S))) return rc;
+    if ((rc = make_tmap_16(&p.tm_v, pr.work + pr.wl.off_v + h0, pr.BH, Skv, pr.DP, 128, pr.bf16, pr.S))) return rc;
     if ((rc = make_tmap_16(&p.tm_do, pr.work + pr.wl.off_do, pr.BH, pr.S, pr.DP, 128, pr.bf16))) return rc;
     if ((rc = make_tmap_f32(&p.tm_dq, dQ, pr.BH, pr.S, pr.D))) return rc;
-    if ((rc = make_tmap_f32(&p.tm_dk, dK, pr.BH, pr.S, pr.D))) return rc;
-    if ((rc = make_tmap_f32(&p.tm_dv, dV, pr.BH, pr.S, pr.D))) return rc;
-    p.lse_log2 = lse2; p.delta = delta; p.dQ = dQ; p.dK = dK; p.dV = dV;
-    p.BH = pr.BH; p.S = pr.S; p.D = pr.D; p.scale = pr.scale; p.scale_log2 = pr.scale_log2; p.bf16 = pr.bf16;
+    if ((rc = make_tmap_f32(&p.tm_dk, dK + e0, pr.BH, Skv, pr.D, pr.S))) return rc;
+    if ((rc = make_tmap_f32(&p.tm_dv, dV + e0, pr.BH, Skv, pr.D, pr.S))) return rc;
+    p.lse_log2 = lse2; p.delta = delta; p.dQ = dQ; p.dK = dK + e0; p.dV = dV + e0;
+    p.BH = pr.BH; p.S_q = pr.S; p.S_kv = Skv; p.D = pr.D; p.scale = pr.scale; p.scale_log2 = pr.scale_log2; p.bf16 = pr.bf16;
     p.range = pr.range()->sc;
     p.timeline = getenv("FA2_TL_FWD_ONLY") ? nullptr : g_timeline;     // (timeline builds: both kernels share the buffer)
     ProfScope prof(3, st);
@@ -575,6 +593,236 @@ int host_worker(const HostJob& job, int dev, int bh0, int count, float* ms_out, 
     return rc;
 }
 
+// ------------------------------------------------------------------------------------------
+// sequence-split path: G = G_bh x G_s devices; a group of G_s devices shares a slab range and splits its rows
+// ------------------------------------------------------------------------------------------
+// Used when there are fewer (b,h) slabs than devices (or an uneven handful): within a group every device holds the
+// group's slabs in full, runs the FORWARD on its own range of query rows (K / V replicated, no exchange) and the
+// BACKWARD on the same range of key/value rows against all query rows.  That leaves one partial dQ per device:
+// the only collective of the whole design, a reduce-scatter over the group done by P2P loads across NVLink
+// (dq_peer_reduce_kernel), after an all-gather of the 2 x S floats per slab of D_i and LSE * log2(e) the forward
+// ranges produced (peer copies).  Each device returns O / LSE / dQ / dK / dV rows of its own range only.
+// Inputs are replicated over PCIe (each device of a group uploads the group's slabs), which costs end-to-end time;
+// what the split buys is kernel time when B*H cannot occupy the devices.
+struct HostBarrier {
+    std::mutex mu;
+    std::condition_variable cv;
+    int n, waiting = 0;
+    unsigned gen = 0;
+    explicit HostBarrier(int n_) : n(n_) {}
+    void arrive_and_wait() {
+        std::unique_lock<std::mutex> lk(mu);
+        const unsigned g = gen;
+        if (++waiting == n) { waiting = 0; ++gen; cv.notify_all(); }
+        else cv.wait(lk, [&] { return gen != g; });
+    }
+};
+
+// Row range of part `part` of `parts` over S rows, boundaries on multiples of 256 rows (one forward work item).
+void seq_range(int S, int parts, int part, int* r0, int* r1) {
+    auto cut = [&](int i) {
+        if (i <= 0) return 0;
+        if (i >= parts) return S;
+        long long x = (static_cast<long long>(S) * i / parts + 128) / 256 * 256;
+        return static_cast<int>(x > S ? S : x);
+    };
+    *r0 = cut(part);
+    *r1 = cut(part + 1);
+}
+
+// (G_bh, G_s) for BH slabs on G devices: the divisor of G that minimises the largest per-device load, preferring the
+// plain slab split.  FA2_SEQ_SPLIT=k forces G_s = k (k must divide G).
+void choose_split(int BH, int S, int G, int* g_bh, int* g_s) {
+    int forced = 0;
+    if (const char* e = getenv("FA2_SEQ_SPLIT")) forced = atoi(e);
+    int best_bh = G < BH ? G : BH, best_s = 1;
+    double best = 1e30;
+    for (int gb = G; gb >= 1; --gb) {          // descending: among equal loads, the least replication (largest G_bh) wins
+        if (G % gb) continue;
+        const int gs = G / gb;
+        if (gb > BH || gs > 8 || (gs > 1 && S / gs < 256)) continue;
+        if (forced > 0 && gs != forced) continue;
+        const double load = static_cast<double>((BH + gb - 1) / gb) / gs * (gs > 1 ? 1.05 : 1.0);
+        if (load < best - 1e-12) { best = load; best_bh = gb; best_s = gs; }
+    }
+    if (best > 1e29) { best_bh = G < BH ? G : BH; best_s = 1; }      // nothing admissible (e.g. forced value does not divide G)
+    *g_bh = best_bh;
+    *g_s = best_s;
+}
+
+struct SeqShared {                  // what the devices of one call publish to each other
+    std::vector<float*> delta, lse2, dq;       // per device: workspace D_i / LSE*log2e (full rows), partial dQ
+    std::vector<cudaEvent_t> ev_side, ev_bwd;  // "my D_i / LSE rows are final", "my backward kernel is done"
+    std::vector<int> rc;
+    std::vector<std::string> err;
+    std::vector<float> ms;
+    std::atomic<bool> failed{false};
+};
+
+int host_dispatch_seqsplit(const HostJob& job, int G_bh, int G_s, float* kernel_ms) {
+    const int G = G_bh * G_s, BH = job.B * job.H, S = job.S, D = job.D;
+    const bool fwd = job.mode != FA2_MODE_BACKWARD, bwd = job.mode != FA2_MODE_FORWARD;
+    int prev_dev = 0;
+    cudaGetDevice(&prev_dev);
+    // peer access inside every group (NVLink P2P loads of the dQ reduce and the side-input copies)
+    for (int d = 0; d < G; ++d) {
+        cudaSetDevice(d);
+        for (int q = d / G_s * G_s; q < d / G_s * G_s + G_s; ++q) {
+            if (q == d) continue;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, d, q);
+            if (!can) { cudaSetDevice(prev_dev); return fail(FA2_ERR_UNSUPPORTED, "sequence split needs peer access between devices %d and %d", d, q); }
+            const cudaError_t e = cudaDeviceEnablePeerAccess(q, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cudaSetDevice(prev_dev); return fail(FA2_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d -> %d): %s", d, q, cudaGetErrorString(e)); }
+            cudaGetLastError();
+        }
+    }
+    SeqShared sh;
+    sh.delta.assign(G, nullptr); sh.lse2.assign(G, nullptr); sh.dq.assign(G, nullptr);
+    sh.ev_side.assign(G, nullptr); sh.ev_bwd.assign(G, nullptr);
+    sh.rc.assign(G, 0); sh.err.assign(G, ""); sh.ms.assign(G, 0.f);
+    HostBarrier bar(G);
+
+    auto worker = [&](int d) {
+        const int gb = d / G_s, gs = d % G_s;
+        int bh0 = 0, cnt = 0, r0 = 0, r1 = 0;
+        fa2_partition(BH, G_bh, gb, &bh0, &cnt);
+        seq_range(S, G_s, gs, &r0, &r1);
+        const RowRange rr{r0, r1};
+        const size_t slab = static_cast<size_t>(S) * D, n = slab * cnt, nl = static_cast<size_t>(S) * cnt;
+        const size_t off = static_cast<size_t>(bh0) * slab, offl = static_cast<size_t>(bh0) * S;
+        std::unique_lock<std::mutex> device_lock(g_pipes[d].mu);        // one host call per device at a time
+        cudaStream_t st = nullptr;
+        cudaEvent_t k0 = nullptr, k1 = nullptr;
+        float *dQ_ = nullptr, *dK_ = nullptr, *dV_ = nullptr, *dO_ = nullptr, *dQin = nullptr, *dKin = nullptr, *dVin = nullptr,
+              *dOut = nullptr, *dL = nullptr;
+        Prepared pr;
+        // phase A: upload, cast, forward on the own query rows, side inputs of the own rows
+        auto phase_a = [&]() -> int {
+            FA2_CUDA(cudaSetDevice(d));
+            FA2_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+            FA2_CUDA(cudaEventCreate(&k0));
+            FA2_CUDA(cudaEventCreate(&k1));
+            FA2_CUDA(cudaEventCreateWithFlags(&sh.ev_side[d], cudaEventDisableTiming));
+            FA2_CUDA(cudaEventCreateWithFlags(&sh.ev_bwd[d], cudaEventDisableTiming));
+            const size_t tb = align_up(n * 4, 1024), lb = align_up(nl * 4, 1024);
+            void* base = nullptr;
+            int rc = arena_reserve(g_io, d, 4 * tb + lb + (bwd ? 4 * tb : 0), &base);
+            if (rc) return rc;
+            uint8_t* b8 = static_cast<uint8_t*>(base);
+            dQin = reinterpret_cast<float*>(b8); dKin = reinterpret_cast<float*>(b8 + tb); dVin = reinterpret_cast<float*>(b8 + 2 * tb);
+            dOut = reinterpret_cast<float*>(b8 + 3 * tb); dL = reinterpret_cast<float*>(b8 + 4 * tb);
+            if (bwd) {
+                dO_ = reinterpret_cast<float*>(b8 + 4 * tb + lb); dQ_ = reinterpret_cast<float*>(b8 + 5 * tb + lb);
+                dK_ = reinterpret_cast<float*>(b8 + 6 * tb + lb); dV_ = reinterpret_cast<float*>(b8 + 7 * tb + lb);
+            }
+            if ((rc = prepare(&pr, 1, cnt, S, D, job.precision, bwd))) return rc;
+            FA2_CUDA(warm_fwd());
+            FA2_CUDA(warm_bwd());
+            sh.delta[d] = reinterpret_cast<float*>(pr.work + pr.wl.off_delta);
+            sh.lse2[d] = reinterpret_cast<float*>(pr.work + pr.wl.off_lse2);
+            sh.dq[d] = dQ_;
+            FA2_CUDA(cudaMemcpyAsync(dQin, job.Q + off, n * 4, cudaMemcpyHostToDevice, st));
+            FA2_CUDA(cudaMemcpyAsync(dKin, job.K + off, n * 4, cudaMemcpyHostToDevice, st));
+            FA2_CUDA(cudaMemcpyAsync(dVin, job.V + off, n * 4, cudaMemcpyHostToDevice, st));
+            if (bwd) FA2_CUDA(cudaMemcpyAsync(dO_, job.dO + off, n * 4, cudaMemcpyHostToDevice, st));
+            if (job.mode == FA2_MODE_BACKWARD) {
+                FA2_CUDA(cudaMemcpyAsync(dOut, job.O_in + off, n * 4, cudaMemcpyHostToDevice, st));
+                FA2_CUDA(cudaMemcpyAsync(dL, job.LSE_in + offl, nl * 4, cudaMemcpyHostToDevice, st));
+            }
+            FA2_CUDA(cudaEventRecord(k0, st));
+            if ((rc = run_cast(pr, dQin, dKin, dVin, st))) return rc;
+            if (fwd && (rc = run_fwd_main(pr, dOut, dL, st, nullptr, nullptr, 0, &rr))) return rc;
+            if (bwd) {
+                // dO cast + dQ zero-fill (and dO's scale decision) over ALL rows; D_i and LSE*log2e over the rows whose
+                // O / LSE this device has: its own range after a forward here, everything in backward-only mode
+                if ((rc = run_bwd_prepass(pr, dOut, dO_, dL, dQ_, 1, st))) return rc;
+                if ((rc = run_bwd_prepass(pr, dOut, dO_, dL, dQ_, 2, st, fwd ? &rr : nullptr))) return rc;
+                if ((rc = run_fix_do(pr, dO_, st))) return rc;
+            }
+            FA2_CUDA(cudaEventRecord(sh.ev_side[d], st));
+            return FA2_OK;
+        };
+        // phase B: gather the peers' D_i / LSE rows, backward on the own key/value rows
+        auto phase_b = [&]() -> int {
+            if (!bwd) return FA2_OK;
+            if (fwd) {
+                for (int q = gb * G_s; q < gb * G_s + G_s; ++q) {
+                    if (q == d) continue;
+                    int q0, q1;
+                    seq_range(S, G_s, q % G_s, &q0, &q1);
+                    if (q1 <= q0) continue;
+                    FA2_CUDA(cudaStreamWaitEvent(st, sh.ev_side[q], 0));
+                    const size_t w = static_cast<size_t>(q1 - q0) * 4, pitch = static_cast<size_t>(S) * 4;
+                    FA2_CUDA(cudaMemcpy2DAsync(sh.delta[d] + q0, pitch, sh.delta[q] + q0, pitch, w, cnt, cudaMemcpyDefault, st));
+                    FA2_CUDA(cudaMemcpy2DAsync(sh.lse2[d] + q0, pitch, sh.lse2[q] + q0, pitch, w, cnt, cudaMemcpyDefault, st));
+                }
+            }
+            int rc = FA2_OK;
+            if (r1 > r0 && (rc = run_bwd_main(pr, dQ_, dK_, dV_, st, &rr))) return rc;
+            FA2_CUDA(cudaEventRecord(sh.ev_bwd[d], st));
+            return FA2_OK;
+        };
+        // phase C: reduce-scatter of dQ (own rows += the peers' partials, read over NVLink), results to the host
+        auto phase_c = [&]() -> int {
+            const size_t w = static_cast<size_t>(r1 - r0) * D * 4, pitch = slab * 4;
+            if (bwd && r1 > r0) {
+                const float* peers[8];
+                int np = 0;
+                for (int q = gb * G_s; q < gb * G_s + G_s; ++q) {
+                    if (q == d) continue;
+                    FA2_CUDA(cudaStreamWaitEvent(st, sh.ev_bwd[q], 0));
+                    peers[np++] = sh.dq[q] + static_cast<size_t>(r0) * D;
+                }
+                FA2_CUDA(launch_dq_peer_reduce(dQ_ + static_cast<size_t>(r0) * D, peers, np, static_cast<size_t>(r1 - r0) * D, slab, cnt, st));
+            }
+            FA2_CUDA(cudaEventRecord(k1, st));
+            if (r1 > r0) {
+                const size_t e0 = static_cast<size_t>(r0) * D;
+                if (fwd) {
+                    FA2_CUDA(cudaMemcpy2DAsync(job.O + off + e0, pitch, dOut + e0, pitch, w, cnt, cudaMemcpyDeviceToHost, st));
+                    FA2_CUDA(cudaMemcpy2DAsync(job.LSE + offl + r0, static_cast<size_t>(S) * 4, dL + r0, static_cast<size_t>(S) * 4,
+                                               static_cast<size_t>(r1 - r0) * 4, cnt, cudaMemcpyDeviceToHost, st));
+                }
+                if (bwd) {
+                    FA2_CUDA(cudaMemcpy2DAsync(job.dQ + off + e0, pitch, dQ_ + e0, pitch, w, cnt, cudaMemcpyDeviceToHost, st));
+                    FA2_CUDA(cudaMemcpy2DAsync(job.dK + off + e0, pitch, dK_ + e0, pitch, w, cnt, cudaMemcpyDeviceToHost, st));
+                    FA2_CUDA(cudaMemcpy2DAsync(job.dV + off + e0, pitch, dV_ + e0, pitch, w, cnt, cudaMemcpyDeviceToHost, st));
+                }
+            }
+            FA2_CUDA(cudaStreamSynchronize(st));
+            FA2_CUDA(cudaEventElapsedTime(&sh.ms[d], k0, k1));
+            return FA2_OK;
+        };
+        // every device reaches every barrier, whatever failed (a peer waiting for an event would hang otherwise)
+        auto step = [&](const std::function<int()>& f) {
+            if (!sh.failed.load() && sh.rc[d] == 0) {
+                const int rc = f();
+                if (rc) { sh.rc[d] = rc; sh.err[d] = g_last_error; sh.failed.store(true); }
+            }
+            bar.arrive_and_wait();
+        };
+        step(phase_a);
+        step(phase_b);
+        step(phase_c);
+        if (st) cudaStreamSynchronize(st);
+        bar.arrive_and_wait();                   // nobody frees or reuses a buffer a peer may still be reading
+        for (cudaEvent_t e : {k0, k1, sh.ev_side[d], sh.ev_bwd[d]}) if (e) cudaEventDestroy(e);
+        if (st) cudaStreamDestroy(st);
+    };
+    std::vector<std::thread> th;
+    for (int d = 0; d < G; ++d) th.emplace_back(worker, d);
+    for (auto& t : th) t.join();
+    cudaSetDevice(prev_dev);
+    float mx = 0.f;
+    for (int d = 0; d < G; ++d) {
+        if (sh.rc[d]) return fail(sh.rc[d], "device %d: %s", d, sh.err[d].c_str());
+        if (sh.ms[d] > mx) mx = sh.ms[d];
+    }
+    if (kernel_ms) *kernel_ms = mx;
+    return FA2_OK;
+}
+
 int host_dispatch(const HostJob& job, int n_gpus, float* kernel_ms) {
     int rc = check_shape(job.B, job.H, job.S, job.D);
     if (rc) return rc;
@@ -588,6 +836,11 @@ int host_dispatch(const HostJob& job, int n_gpus, float* kernel_ms) {
     if (n_gpus <= 0) n_gpus = 1;
     if (n_gpus > ndev) return fail(FA2_ERR_INVALID_ARGUMENT, "n_gpus=%d but only %d device(s) visible", n_gpus, ndev);
     const int BH = job.B * job.H;
+    if (n_gpus > 1) {
+        int g_bh = n_gpus, g_s = 1;
+        choose_split(BH, job.S, n_gpus, &g_bh, &g_s);
+        if (g_s > 1) return host_dispatch_seqsplit(job, g_bh, g_s, kernel_ms);
+    }
     if (n_gpus > BH) n_gpus = BH;
     int prev_dev = 0;
     cudaGetDevice(&prev_dev);
@@ -644,6 +897,19 @@ int fa2_plan_chunks(int count, int S, int D, int mode, int* sizes, int max_chunk
     const std::vector<int> v = plan_chunks(count, S, D, mode != FA2_MODE_BACKWARD, mode != FA2_MODE_FORWARD);
     for (size_t i = 0; i < v.size() && static_cast<int>(i) < max_chunks; ++i) sizes[i] = v[i];
     return static_cast<int>(v.size());
+}
+
+int fa2_plan_split(int BH, int S, int n_gpus, int* g_bh, int* g_s) {
+    if (BH <= 0 || S <= 0 || n_gpus <= 0 || !g_bh || !g_s) return fail(FA2_ERR_INVALID_ARGUMENT, "bad split request");
+    if (n_gpus == 1) { *g_bh = 1; *g_s = 1; return FA2_OK; }
+    choose_split(BH, S, n_gpus, g_bh, g_s);
+    return FA2_OK;
+}
+
+int fa2_seq_range(int S, int parts, int part, int* r0, int* r1) {
+    if (S <= 0 || parts <= 0 || part < 0 || part >= parts || !r0 || !r1) return fail(FA2_ERR_INVALID_ARGUMENT, "bad range request");
+    seq_range(S, parts, part, r0, r1);
+    return FA2_OK;
 }
 
 int fa2_device_count(void) {

@@ -107,11 +107,12 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
     // work on neighbouring KV tiles of the same few heads (Q / dO reuse in L2).  All items have n_tiles steps, so
     // every per-step barrier parity comes from the running step count G = it * n_tiles + i and every per-item
     // parity from it (items this CTA has started).
-    const int n_tiles = (p.S + BT - 1) / BT;       // same count for KV and Q tiles
-    const int n_work = p.BH * n_tiles;
+    const int n_tiles = (p.S_q + BT - 1) / BT;     // Q tiles = steps of every work item
+    const int n_kvt = (p.S_kv + BT - 1) / BT;      // KV tiles of a slab = work items per slab
+    const int n_work = p.BH * n_kvt;
     // Every KV tile of a (b,h) slab walks the Q tiles in a different rotation, so that at any moment the
     // concurrently running CTAs reduce-add into DIFFERENT dQ tiles (no same-address contention in L2).
-    auto q_row_at = [&](int kv_tile, int i) { int t = i + kv_tile; if (t >= n_tiles) t -= n_tiles; return t * BT; };
+    auto q_row_at = [&](int kv_tile, int i) { return ((i + kv_tile) % n_tiles) * BT; };
     if (warp == TMA_WARP && lane == 0) {
         tma_prefetch_desc(&p.tm_q);
         tma_prefetch_desc(&p.tm_k);
@@ -156,7 +157,7 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
         setmaxnreg_dec<40>();
         int it = 0;
         for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
-        const int bh = w / n_tiles, kv_tile = w % n_tiles, kv_row0 = kv_tile * BT;
+        const int bh = w / n_kvt, kv_tile = w % n_kvt, kv_row0 = kv_tile * BT;
         auto q_row_of = [&](int i) { return q_row_at(kv_tile, i); };
         mbar_wait(kv_empty, (it & 1) ^ 1);                     // previous item's MMAs are done with K / V
         if (elect_one()) {
@@ -179,8 +180,8 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
 #pragma unroll
             for (int r = 0; r < BT / 32; ++r) {
                 const int row = q_row_of(i) + r * 32 + lane;
-                const bool ok = row < p.S;
-                const size_t g = static_cast<size_t>(bh) * p.S + (ok ? row : 0);
+                const bool ok = row < p.S_q;
+                const size_t g = static_cast<size_t>(bh) * p.S_q + (ok ? row : 0);
                 r_lse[r] = ok ? __ldg(p.lse_log2 + g) : INFINITY;
                 r_dl[r] = ok ? __ldg(p.delta + g) * delta_mul : 0.0f;
             }
@@ -341,10 +342,10 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
 
         int it = 0;
         for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
-        const int bh = w / n_tiles, kv_row0 = (w % n_tiles) * BT;
+        const int bh = w / n_kvt, kv_row0 = (w % n_kvt) * BT;
         const int G0 = it * n_tiles;
-        const bool ragged_kv = kv_row0 + BT > p.S;                          // CTA-uniform: only the last KV tile of a slab
-        const uint32_t kv_keep = (kv_row0 + n < p.S) ? 0xffffffffu : 0u;   // padded KV lane: P = dS = 0
+        const bool ragged_kv = kv_row0 + BT > p.S_kv;                          // CTA-uniform: only the last KV tile of a slab
+        const uint32_t kv_keep = (kv_row0 + n < p.S_kv) ? 0xffffffffu : 0u;   // padded KV lane: P = dS = 0
 #ifdef FA2_TIMELINE
         if (threadIdx.x == 0 && p.timeline) {
             uint32_t smid;
@@ -506,7 +507,7 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
 
         int it = 0;
         for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
-        const int bh = w / n_tiles, kv_tile = w % n_tiles;
+        const int bh = w / n_kvt, kv_tile = w % n_kvt;
         auto q_row_of = [&](int i) { return q_row_at(kv_tile, i); };
         auto put_chunk = [&](const uint32_t (&rc)[32], int chunk, int i) {
             const float dq_mul = p.range != nullptr ? ldg_scalar_volatile(p.range + kDqMul) : p.scale;   // 1 / sqrt(D), inverse scales
@@ -573,7 +574,7 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
 
 cudaError_t launch_bwd(const BwdParams& p, cudaStream_t st) {
     const int DP = padded_head_dim(p.D);
-    const int n_tiles = (p.S + BT - 1) / BT;
+    const int n_tiles = (p.S_kv + BT - 1) / BT;
     // persistent: one CTA per SM (or fewer when there is less work), each walks its share of the work items
     static int sm_count[64] = {0};
     int dev = 0;

@@ -47,7 +47,11 @@ struct FwdParams {
     CUtensorMap tm_o;   // fp32 [BH][S][D], box {32, 128, 1}, 128B swizzle (store target)
     float* O;           // fp32 [BH][S][D]
     float* LSE;         // fp32 [BH][S] natural log
-    int BH, S, D;
+    // Geometry.  One launch covers S_q query rows of every slab against S_kv key/value rows.  Normally
+    // S_q = S_kv = q_pitch = S; the sequence-split path launches a row range [r0, r1) of every slab: the tensor maps
+    // and the row-indexed pointers (LSE, dO, delta, lse_log2) are pre-offset by r0 and q_pitch stays the full S.
+    int BH, S_q, S_kv, q_pitch, D;
+    long long donor_rows;   // rows of dO / dQ the donor warps cast / zero-fill (all BH * S rows, whatever S_q is)
     float scale_log2;   // log2(e) / sqrt(D)
     float scale;        // 1 / sqrt(D)
     int bf16;
@@ -75,7 +79,9 @@ struct BwdParams {
     float* dQ;              // fp32 [BH][S][D], zeroed by the pre-pass, reduce-added here
     float* dK;
     float* dV;
-    int BH, S, D;
+    // One launch covers S_kv key/value rows of every slab (work items = their 128-row tiles; the sequence-split path
+    // passes a row range through pre-offset tensor maps) against all S_q query rows.
+    int BH, S_q, S_kv, D;
     float scale_log2;
     float scale;
     int bf16;
@@ -122,7 +128,11 @@ cudaError_t launch_cast_qkv(const float* Q, const float* K, const float* V, void
 cudaError_t launch_bwd_prepass(const float* O, const float* dO, const float* LSE, void* dOh, float* delta,
                                float* lse_log2, float* dQ_zero, size_t rows, int D, int DP, int bf16,
                                int parts /* 1: dO cast + dQ zero, 2: D_i + LSE, 3: both */, RangeBlock* rb,
-                               float scale, cudaStream_t st);
+                               float scale, cudaStream_t st, unsigned range_rows = 1, unsigned pitch_rows = 1);
+// dQ reduce-scatter of the sequence-split path: own[i] += sum over peers of peer[i] on `cnt` row ranges of
+// `seg_floats` floats, `pitch_floats` apart; the peer pointers are other GPUs' memory read over NVLink (P2P loads).
+cudaError_t launch_dq_peer_reduce(float* own, const float* const* peers, int n_peers, size_t seg_floats,
+                                  size_t pitch_floats, int cnt, cudaStream_t st);
 // Small problems: ONE cooperative launch measures max|x| of Q, K, V (and dO), decides the scales behind a grid
 // barrier and casts with them (second read served by L2); with dO it also zero-fills dQ.  No re-cast kernels needed.
 cudaError_t launch_cast_small(const float* Q, const float* K, const float* V, const float* dO, void* Qh, void* Kh,

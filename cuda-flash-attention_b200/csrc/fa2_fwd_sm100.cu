@@ -102,10 +102,10 @@ fa2_fwd_kernel(const __grid_constant__ FwdParams p) {
     //   it        work items this CTA has started           (q_empty, Q tile 0, o_full[0])
     //   n1        of those, the ones whose second Q tile exists (Q tile 1, o_full[1])
     //   it * n_kv + j   KV ring position / tile 0 step;   n1 * n_kv + j   tile 1 step
-    const int q_blocks = (p.S + 2 * BM - 1) / (2 * BM);
+    const int q_blocks = (p.S_q + 2 * BM - 1) / (2 * BM);
     const int n_work = p.BH * q_blocks;
-    const int n_kv = (p.S + BN - 1) / BN;
-    auto tiles_of = [&](int w) { return ((w % q_blocks) * (2 * BM) + BM < p.S) ? 2 : 1; };
+    const int n_kv = (p.S_kv + BN - 1) / BN;
+    auto tiles_of = [&](int w) { return ((w % q_blocks) * (2 * BM) + BM < p.S_q) ? 2 : 1; };
 
     if (warp == TMA_WARP && lane == 0) {
         tma_prefetch_desc(&p.tm_q);
@@ -276,7 +276,7 @@ fa2_fwd_kernel(const __grid_constant__ FwdParams p) {
         if (FUSED && p.dOh != nullptr) {
             constexpr int LPR = DP / 8, RPW = 32 / LPR, U = 2;     // lanes per row, rows per warp pass, passes in flight
             const int sub = lane / LPR, l = lane % LPR, col = l * 8;
-            const size_t rows = static_cast<size_t>(p.BH) * p.S;
+            const size_t rows = static_cast<size_t>(p.donor_rows);
             const size_t wid = static_cast<size_t>(blockIdx.x) * 2 + (warp - 10), nw = static_cast<size_t>(gridDim.x) * 2;
             uint4* dOh = static_cast<uint4*>(p.dOh);
             float4* dq = reinterpret_cast<float4*>(p.dQ_zero);
@@ -365,7 +365,7 @@ fa2_fwd_kernel(const __grid_constant__ FwdParams p) {
                 for (int c = 0; c < 4; ++c) tmem_ld32(t_s + c * 32, sr[c]);
                 tmem_wait_ld();
 
-                const int valid = p.S - j * BN;     // columns >= valid are padding in the last tile
+                const int valid = p.S_kv - j * BN;  // columns >= valid are padding in the last tile
                 if (valid < BN) {
 #pragma unroll
                     for (int c = 0; c < 4; ++c)
@@ -441,14 +441,14 @@ fa2_fwd_kernel(const __grid_constant__ FwdParams p) {
             // fused forward+backward: this thread also forms D_i = rowsum(dO o O) for its row (the reference's
             // D_computation_reduction_kernel, f-attn2-backward.cu:342-380) while O is in registers; the dO row is
             // fetched before the wait for the last P V so that its latency hides there.
-            const bool row_ok = q_row < p.S;
+            const bool row_ok = q_row < p.S_q;
             // (rows past S read row 0 of the slab: a valid address whose result is never stored)
             // Row-per-thread global loads cost the LSU one wavefront per lane per instruction whatever their width
             // (measured: with 128-bit loads the four chunks added 5.7K cycles to every epilogue, with 256-bit loads
             // 3.5K; tools/timeline_fwd.py ... fused), hence LDG.256.  Variants that read the staged O tile with
             // coalesced dO loads, or request dO further ahead, either stall on the proxy fence before the TMA store
             // (it waits for the thread's outstanding loads, ~2500 cycles each) or spill.
-            const float* do_row = (FUSED ? p.dO : p.O) + (static_cast<size_t>(bh) * p.S + (row_ok ? q_row : 0)) * p.D;
+            const float* do_row = (FUSED ? p.dO : p.O) + (static_cast<size_t>(bh) * p.q_pitch + (row_ok ? q_row : 0)) * p.D;
             float dov[4][8];                                            // dO columns of the chunk being reduced
             if constexpr (FUSED) {
 #pragma unroll
@@ -498,7 +498,7 @@ fa2_fwd_kernel(const __grid_constant__ FwdParams p) {
                 }
             }
             if (row_ok) {
-                const size_t g = static_cast<size_t>(bh) * p.S + q_row;
+                const size_t g = static_cast<size_t>(bh) * p.q_pitch + q_row;
                 const float lse = m_ref * (p.range != nullptr ? __ldg(p.range + kScaleLse) : p.scale) + logf(l_run);
                 p.LSE[g] = lse;
                 if (FUSED && p.delta != nullptr) {
@@ -524,7 +524,7 @@ fa2_fwd_kernel(const __grid_constant__ FwdParams p) {
 
 cudaError_t launch_fwd(const FwdParams& p, cudaStream_t st) {
     const int DP = padded_head_dim(p.D);
-    const int q_blocks = (p.S + 2 * BM - 1) / (2 * BM);
+    const int q_blocks = (p.S_q + 2 * BM - 1) / (2 * BM);
     // persistent: one CTA per SM (or fewer when there is less work), each walks its share of the work items
     static int sm_count[64] = {0};
     int dev = 0;

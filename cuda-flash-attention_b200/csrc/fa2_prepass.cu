@@ -190,7 +190,10 @@ template <int LANES_PER_ROW, int PARTS>
 __global__ void __launch_bounds__(256)
 bwd_prepass_kernel(const float* __restrict__ O, const float* __restrict__ dO, const float* __restrict__ LSE,
                    uint4* __restrict__ dOh, float* __restrict__ delta, float* __restrict__ lse_log2,
-                   float4* __restrict__ dQ, size_t rows, int D, int DP, int bf16, RangeBlock* rb, float scale) {
+                   float4* __restrict__ dQ, size_t rows, int D, int DP, int bf16, RangeBlock* rb, float scale,
+                   unsigned range_rows, unsigned pitch_rows) {
+    // rows are counted over a row range of every slab: range_rows consecutive rows, slabs pitch_rows apart (the
+    // sequence-split path; pointers come pre-offset to the first row of the range).  Normally range_rows == pitch_rows.
     constexpr int ROWS_PER_WARP = 32 / LANES_PER_ROW;
     const int lane = threadIdx.x & 31;
     const int sub = lane / LANES_PER_ROW;          // which row of the warp's group
@@ -200,9 +203,10 @@ bwd_prepass_kernel(const float* __restrict__ O, const float* __restrict__ dO, co
     const int vec_per_row = DP >> 3;
     float m = 0.0f;
     for (size_t base = warp_global * ROWS_PER_WARP; base < rows; base += n_warps * ROWS_PER_WARP) {
-        const size_t row = base + sub;
+        const size_t lrow = base + sub;
+        const size_t row = (range_rows == pitch_rows) ? lrow : (lrow / range_rows) * pitch_rows + lrow % range_rows;
         float acc = 0.f;
-        if (row < rows) {
+        if (lrow < rows) {
             const int col = l * 8;
             uint4 out = make_uint4(0u, 0u, 0u, 0u);
             if (col < D) {
@@ -231,7 +235,7 @@ bwd_prepass_kernel(const float* __restrict__ O, const float* __restrict__ dO, co
         if (PARTS & 2) {
 #pragma unroll
             for (int off = LANES_PER_ROW / 2; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-            if (row < rows && l == 0) {
+            if (lrow < rows && l == 0) {
                 delta[row] = acc;
                 lse_log2[row] = LSE[row] * 1.4426950408889634f;
             }
@@ -240,6 +244,25 @@ bwd_prepass_kernel(const float* __restrict__ O, const float* __restrict__ dO, co
     if ((PARTS & 1) && rb != nullptr) {
         block_amax(m, rb->amax[3]);
         if (threadIdx.x == 0 && range_last_arrival(&rb->ticket[1], gridDim.x)) decide_do(rb, D, bf16, scale);
+    }
+}
+
+// Sequence-split backward: every GPU of a group holds a partial dQ (its KV range's contribution to ALL query rows); the
+// owner of a query-row range adds the other partials' rows to its own, reading them straight out of the peers' memory
+// (NVLink / NVSwitch P2P loads; the owner's range is read by nobody else, so the sum is formed in place).
+struct PeerPtrs { const float4* p[8]; };
+__global__ void __launch_bounds__(256)
+dq_peer_reduce_kernel(float4* __restrict__ own, PeerPtrs peers, int n_peers, size_t seg_vec, size_t pitch_vec, int cnt) {
+    const size_t total = seg_vec * cnt;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const size_t idx = (i / seg_vec) * pitch_vec + i % seg_vec;
+        float4 acc = own[idx];
+        for (int q = 0; q < n_peers; ++q) {
+            const float4 v = __ldcg(peers.p[q] + idx);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        own[idx] = acc;
     }
 }
 
@@ -286,6 +309,20 @@ cudaError_t launch_cast_small(const float* Q, const float* K, const float* V, co
                                        dim3(256), args, 0, st);
 }
 
+cudaError_t launch_dq_peer_reduce(float* own, const float* const* peers, int n_peers, size_t seg_floats,
+                                  size_t pitch_floats, int cnt, cudaStream_t st) {
+    if (n_peers <= 0 || cnt <= 0 || seg_floats == 0) return cudaSuccess;
+    if (n_peers > 8 || (seg_floats & 3) || (pitch_floats & 3)) return cudaErrorInvalidValue;
+    PeerPtrs pp{};
+    for (int i = 0; i < n_peers; ++i) pp.p[i] = reinterpret_cast<const float4*>(peers[i]);
+    const size_t total = (seg_floats >> 2) * cnt;
+    size_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    dq_peer_reduce_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(reinterpret_cast<float4*>(own), pp, n_peers,
+                                                                         seg_floats >> 2, pitch_floats >> 2, cnt);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_range_fix_qkv(const float* Q, const float* K, const float* V, void* Qh, void* Kh, void* Vh,
                                  size_t rows, int D, int DP, int bf16, const RangeBlock* rb, cudaStream_t st) {
     range_fix_qkv_kernel<<<dim3(fix_blocks(rows, DP), 3), 256, 0, st>>>(
@@ -301,7 +338,7 @@ cudaError_t launch_range_fix_do(const float* dO, void* dOh, size_t rows, int D, 
 
 cudaError_t launch_bwd_prepass(const float* O, const float* dO, const float* LSE, void* dOh, float* delta,
                                float* lse_log2, float* dQ_zero, size_t rows, int D, int DP, int bf16, int parts,
-                               RangeBlock* rb, float scale, cudaStream_t st) {
+                               RangeBlock* rb, float scale, cudaStream_t st, unsigned range_rows, unsigned pitch_rows) {
     const int lanes = DP >> 3;                    // 8 (DP = 64) or 16 (DP = 128)
     const size_t rows_per_block = (256 / 32) * (32 / lanes);
     size_t blocks = (rows + rows_per_block - 1) / rows_per_block;
@@ -310,7 +347,7 @@ cudaError_t launch_bwd_prepass(const float* O, const float* dO, const float* LSE
     const unsigned g = static_cast<unsigned>(blocks);
     uint4* dh = static_cast<uint4*>(dOh);
     float4* dq = reinterpret_cast<float4*>(dQ_zero);
-#define FA2_PRE(L, P) bwd_prepass_kernel<L, P><<<g, 256, 0, st>>>(O, dO, LSE, dh, delta, lse_log2, dq, rows, D, DP, bf16, rb, scale)
+#define FA2_PRE(L, P) bwd_prepass_kernel<L, P><<<g, 256, 0, st>>>(O, dO, LSE, dh, delta, lse_log2, dq, rows, D, DP, bf16, rb, scale, range_rows, pitch_rows)
     if (lanes == 8) { if (parts == 1) FA2_PRE(8, 1); else if (parts == 2) FA2_PRE(8, 2); else FA2_PRE(8, 3); }
     else            { if (parts == 1) FA2_PRE(16, 1); else if (parts == 2) FA2_PRE(16, 2); else FA2_PRE(16, 3); }
 #undef FA2_PRE

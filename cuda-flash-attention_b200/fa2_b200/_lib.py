@@ -32,6 +32,8 @@ SIGNATURES = {
     "fa2_host_forward_backward": (_i, [_fp] * 9 + [_i] * 6 + [ctypes.POINTER(ctypes.c_float)]),
     "fa2_partition": (_i, [_i, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(_i)]),
     "fa2_plan_chunks": (_i, [_i, _i, _i, _i, ctypes.POINTER(_i), _i]),
+    "fa2_plan_split": (_i, [_i, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(_i)]),
+    "fa2_seq_range": (_i, [_i, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(_i)]),
     "fa2_device_count": (_i, []),
     "fa2_release_workspaces": (_i, []),
     "fa2_profile_enable": (_i, [_i]),

@@ -115,6 +115,20 @@ def partition(BH: int, n_parts: int, part: int) -> Tuple[int, int]:
     return a.value, b.value
 
 
+def plan_split(BH: int, S: int, n_gpus: int) -> Tuple[int, int]:
+    """(g_bh, g_s): groups of devices over the slabs x devices per group over the rows (fa2_plan_split)."""
+    a, b = ctypes.c_int(), ctypes.c_int()
+    check(_lib.load().fa2_plan_split(BH, S, n_gpus, ctypes.byref(a), ctypes.byref(b)))
+    return a.value, b.value
+
+
+def seq_range(S: int, parts: int, part: int) -> Tuple[int, int]:
+    """Row range [r0, r1) of `part` in a sequence split over `parts` devices (fa2_seq_range)."""
+    a, b = ctypes.c_int(), ctypes.c_int()
+    check(_lib.load().fa2_seq_range(S, parts, part, ctypes.byref(a), ctypes.byref(b)))
+    return a.value, b.value
+
+
 def forward(Q, K, V, precision: str = "fp32", stream=None, out=None):
     """O, LSE = FA2 forward on device tensors [B,H,S,D] fp32. LSE is natural-log [B,H,S]."""
     if len(Q.shape) != 4:

@@ -100,6 +100,16 @@ int fa2_partition(int BH, int n_parts, int part, int* bh0, int* count);
  * Pure arithmetic, no GPU needed. */
 int fa2_plan_chunks(int count, int S, int D, int mode, int* sizes, int max_chunks);
 
+/* How the host-pointer entry points lay BH = B*H slabs of S rows over n_gpus devices: *g_bh groups of devices
+ * split the slabs (fa2_partition), the *g_s devices of a group split the ROWS of the group's slabs
+ * (*g_bh * *g_s <= n_gpus).  *g_s == 1 is the plain slab split (the usual case); a sequence split is chosen when
+ * there are fewer slabs than devices or an uneven handful (override: FA2_SEQ_SPLIT=<g_s>).  With *g_s > 1 the
+ * forward runs on a range of query rows per device (K/V replicated), the backward on the same range of key/value
+ * rows, and the group's partial dQ are summed by a reduce-scatter over NVLink -- the only collective of the design.
+ * fa2_seq_range gives part `part`'s row range [*r0, *r1) (boundaries on multiples of 256 rows).  Pure arithmetic. */
+int fa2_plan_split(int BH, int S, int n_gpus, int* g_bh, int* g_s);
+int fa2_seq_range(int S, int parts, int part, int* r0, int* r1);
+
 /* Number of CUDA devices visible to the library (0 without a GPU; never fails). */
 int fa2_device_count(void);
 

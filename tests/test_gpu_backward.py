@@ -363,3 +363,36 @@ def test_cupy_style_arrays_go_through_the_data_ptr_branch(U, monkeypatch):
         assert U.maxerr(U.host(x), w) < tol
     with pytest.raises(ValueError):
         api.forward(q, k, _FakeCuPy(torch.empty(1, 2, 100, 64, device="cuda")), stream=0)
+
+
+@pytest.mark.parametrize("shape,force", [((1, 1, 1024, 64), None), ((1, 3, 1536, 128), "2"), ((2, 1, 700, 32), "2")],
+                         ids=["B1_H1_S1024_D64-auto", "B1_H3_S1536_D128-forced", "B2_H1_S700_D32-forced"])
+def test_host_api_sequence_split_two_gpus(U, shape, force, monkeypatch):
+    """Fewer (b,h) slabs than devices (or FA2_SEQ_SPLIT): the devices of a group split the ROWS -- forward on a range of
+    query rows per device, backward on the same range of key/value rows, partial dQ summed by P2P loads over NVLink
+    (the one collective of the design).  All three modes must reproduce the one-GPU results."""
+    import torch
+    import fa2_b200
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    if force:
+        monkeypatch.setenv("FA2_SEQ_SPLIT", force)
+    B, H, S, D = shape
+    assert fa2_b200.plan_split(B * H, S, 2)[1] == 2
+    Q, K, V, dO = U.randn_case(shape, seed=43)
+    monkeypatch.delenv("FA2_SEQ_SPLIT", raising=False)
+    one, _ = fa2_b200.run_flash_attention(Q, K, V, dO=dO, mode="forward_backward", n_gpus=1)
+    if force:
+        monkeypatch.setenv("FA2_SEQ_SPLIT", force)
+    two, ms = fa2_b200.run_flash_attention(Q, K, V, dO=dO, mode="forward_backward", n_gpus=2)
+    assert ms > 0
+    truth = U.orc.attention_fp64(Q, K, V, dO)
+    for a, b, t, n in zip(one, two, truth, ("O", "LSE", "dQ", "dK", "dV")):
+        assert np.isfinite(b).all(), n
+        assert U.maxerr(b, t) < (U.TOL_LSE if n == "LSE" else U.TOL_GRAD), n
+        assert U.maxerr(a, b) < 2e-4, n                     # same kernels; D_i comes from the pre-pass instead of the fused epilogue
+    (O2, L2), _ = fa2_b200.run_flash_attention(Q, K, V, mode="forward", n_gpus=2)
+    assert np.array_equal(O2, one[0]) and np.array_equal(L2, one[1])          # forward row ranges: same tiles, same bits
+    (dQ3, dK3, dV3), _ = fa2_b200.run_flash_attention(Q, K, V, one[0], one[1], dO=dO, mode="backward", n_gpus=2)
+    for got, t, n in zip((dQ3, dK3, dV3), truth[2:], ("dQ", "dK", "dV")):
+        assert U.maxerr(got, t) < U.TOL_GRAD, n

@@ -62,3 +62,79 @@ def test_two_rank_slab_sharding_matches_unsharded(tmp_path, shape):
     got = np.load(tmp_path / "gathered.npy")
     assert np.array_equal(np.load(tmp_path / "counts.npy"), np.ones(B * H))      # every slab exactly once
     assert np.abs(got - O[0]).max() < 1e-6
+
+
+def _seq_worker(rank, world, port, shape, out_dir):
+    """Sequence-split logic of fa2_host_* (csrc/fa2_api.cu host_dispatch_seqsplit) with numpy standing in for the
+    kernels: rank r runs the forward on ITS query rows (K/V replicated), contributes D_i / LSE of those rows to an
+    all-gather, runs the backward on ITS key/value rows against all query rows, and the partial dQ are summed
+    (the one collective of the design) -- here an all-reduce over gloo, on the device a reduce-scatter over NVLink."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "cuda-flash-attention_b200"))
+    import fa2_b200
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    BH, S, D = shape
+    rng = np.random.default_rng(7)
+    Q, K, V, dO = (rng.standard_normal((BH, S, D)) for _ in range(4))
+    g_bh, g_s = fa2_b200.plan_split(BH, S, world)
+    assert (g_bh, g_s) == (1, world)                              # one slab, two devices -> rows are split
+    r0, r1 = fa2_b200.seq_range(S, g_s, rank)
+    sc = 1.0 / np.sqrt(D)
+    # forward on the own query rows
+    s_own = np.einsum("hqd,hkd->hqk", Q[:, r0:r1], K) * sc
+    lse_own = np.log(np.exp(s_own - s_own.max(-1, keepdims=True)).sum(-1)) + s_own.max(-1)
+    O_own = np.einsum("hqk,hkd->hqd", np.exp(s_own - lse_own[..., None]), V)
+    # all-gather of D_i and LSE (disjoint row ranges: a sum of zero-padded pieces)
+    lse = torch.zeros(BH, S, dtype=torch.float64)
+    delta = torch.zeros(BH, S, dtype=torch.float64)
+    lse[:, r0:r1] = torch.from_numpy(lse_own)
+    delta[:, r0:r1] = torch.from_numpy((dO[:, r0:r1] * O_own).sum(-1))
+    dist.all_reduce(lse)
+    dist.all_reduce(delta)
+    lse, delta = lse.numpy(), delta.numpy()
+    # backward on the own key/value rows against ALL query rows
+    P = np.exp(np.einsum("hqd,hkd->hqk", Q, K[:, r0:r1]) * sc - lse[..., None])
+    dV_own = np.einsum("hqk,hqd->hkd", P, dO)
+    dS = P * (np.einsum("hqd,hkd->hqk", dO, V[:, r0:r1]) - delta[..., None]) * sc
+    dK_own = np.einsum("hqk,hqd->hkd", dS, Q)
+    dQ = torch.from_numpy(np.einsum("hqk,hkd->hqd", dS, K[:, r0:r1]))          # partial: this KV range only
+    dist.all_reduce(dQ)                                                      # <- the dQ reduce
+    full = {n: torch.zeros(BH, S, D, dtype=torch.float64) for n in ("O", "dK", "dV")}
+    for n, a in (("O", O_own), ("dK", dK_own), ("dV", dV_own)):
+        full[n][:, r0:r1] = torch.from_numpy(a)
+        dist.all_reduce(full[n])
+    if rank == 0:
+        np.savez(os.path.join(out_dir, "seq.npz"), dQ=dQ.numpy(), lse=lse, **{n: t.numpy() for n, t in full.items()})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sequence_split_with_dq_reduce_matches_unsplit(tmp_path):
+    from oracle import fa2_oracle as orc
+    shape = (1, 1024, 32)                                 # one (b,h) slab on two devices: rows 0..511 / 512..1023
+    port = _free_port()
+    mp.spawn(_seq_worker, args=(2, port, shape, str(tmp_path)), nprocs=2, join=True)
+    BH, S, D = shape
+    rng = np.random.default_rng(7)
+    Q, K, V, dO = (rng.standard_normal((BH, S, D)) for _ in range(4))
+    tO, tL, tdQ, tdK, tdV = orc.attention_fp64(Q[None], K[None], V[None], dO[None])
+    z = np.load(tmp_path / "seq.npz")
+    for n, want in (("O", tO), ("lse", tL), ("dQ", tdQ), ("dK", tdK), ("dV", tdV)):
+        assert np.abs(z[n] - want[0]).max() < 1e-9, n
+
+
+def test_split_planner_and_row_ranges():
+    import fa2_b200
+    assert fa2_b200.plan_split(256, 4096, 8) == (8, 1)          # config C: plenty of slabs, plain slab split
+    assert fa2_b200.plan_split(16, 16384, 8) == (8, 1)          # config D: two slabs per device, no gain from splitting rows
+    assert fa2_b200.plan_split(4, 16384, 8) == (4, 2)           # fewer slabs than devices
+    assert fa2_b200.plan_split(1, 16384, 8) == (1, 8)
+    assert fa2_b200.plan_split(12, 8192, 8) == (4, 2)           # 12 slabs on 8 devices: 3 slabs x half the rows beat 2 / 1
+    assert fa2_b200.plan_split(1, 300, 8) == (1, 1)             # too short to split: one device
+    assert fa2_b200.plan_split(3, 4096, 1) == (1, 1)
+    for S, parts in ((16384, 8), (4096, 2), (1000, 2), (700, 2)):
+        ranges = [fa2_b200.seq_range(S, parts, p) for p in range(parts)]
+        assert ranges[0][0] == 0 and ranges[-1][1] == S
+        assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))         # contiguous, disjoint, complete
+        assert all(r[0] % 256 == 0 for r in ranges)
