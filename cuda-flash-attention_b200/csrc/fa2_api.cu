@@ -630,24 +630,31 @@ void seq_range(int S, int parts, int part, int* r0, int* r1) {
     *r1 = cut(part + 1);
 }
 
-// (G_bh, G_s) for BH slabs on G devices: the divisor of G that minimises the largest per-device load, preferring the
-// plain slab split.  FA2_SEQ_SPLIT=k forces G_s = k (k must divide G).
+// (G_bh, G_s) for BH slabs on G devices.  With at least one slab per device the plain slab split is used: the host
+// path is PCIe-bound and a sequence split replicates a group's inputs on each of its devices.  With fewer slabs than
+// devices the rows are split only if that shortens the kernels: the persistent kernels need ceil(items / SMs) rounds
+// of one work item each (an item walks all S / 128 tiles of the other operand), so splitting rows pays once a
+// device's share exceeds one round -- a single slab has S / 256 forward items, i.e. beyond S = 32k.
+// FA2_SEQ_SPLIT=k forces G_s = k (k must divide G; used by the tests and tools/seq_split_bench.py).
 void choose_split(int BH, int S, int G, int* g_bh, int* g_s) {
     int forced = 0;
     if (const char* e = getenv("FA2_SEQ_SPLIT")) forced = atoi(e);
-    int best_bh = G < BH ? G : BH, best_s = 1;
+    *g_bh = G < BH ? G : BH;
+    *g_s = 1;
+    if (forced <= 0 && BH >= G) return;
+    const int n_sm = 148;
+    const double n_steps = (S + 127) / 128;
     double best = 1e30;
-    for (int gb = G; gb >= 1; --gb) {          // descending: among equal loads, the least replication (largest G_bh) wins
-        if (G % gb) continue;
-        const int gs = G / gb;
-        if (gb > BH || gs > 8 || (gs > 1 && S / gs < 256)) continue;
+    for (int gs = 1; gs <= 8 && gs <= G; gs *= 2) {
+        if (G % gs) continue;
+        const int gb = G / gs < BH ? G / gs : BH;
+        if (gs > 1 && S / gs < 256) continue;
         if (forced > 0 && gs != forced) continue;
-        const double load = static_cast<double>((BH + gb - 1) / gb) / gs * (gs > 1 ? 1.05 : 1.0);
-        if (load < best - 1e-12) { best = load; best_bh = gb; best_s = gs; }
+        const long long c = (BH + gb - 1) / gb, rows = (S + gs - 1) / gs;
+        const long long items_f = c * ((rows + 255) / 256), items_b = c * ((rows + 127) / 128);
+        const double t = ((items_f + n_sm - 1) / n_sm * 1.65 + (items_b + n_sm - 1) / n_sm * 2.15) * n_steps * (gs > 1 ? 1.05 : 1.0);
+        if (t < best - 1e-9) { best = t; *g_bh = gb; *g_s = gs; }
     }
-    if (best > 1e29) { best_bh = G < BH ? G : BH; best_s = 1; }      // nothing admissible (e.g. forced value does not divide G)
-    *g_bh = best_bh;
-    *g_s = best_s;
 }
 
 struct SeqShared {                  // what the devices of one call publish to each other

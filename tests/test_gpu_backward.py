@@ -242,13 +242,14 @@ def test_host_api_two_gpus_match_one_gpu(U):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     Q, K, V, dO = U.randn_case((3, 5, 640, 128), seed=41)          # 15 slabs: 7 + 8
+    assert fa2_b200.plan_split(15, 640, 2) == (2, 1)
     one, _ = fa2_b200.run_flash_attention(Q, K, V, dO=dO, mode="forward_backward", n_gpus=1)
     two, _ = fa2_b200.run_flash_attention(Q, K, V, dO=dO, mode="forward_backward", n_gpus=2)
     for a, b, exact in zip(one, two, (True, True, False, True, True)):
         if exact:
             assert np.array_equal(a, b)
         else:
-            assert U.maxerr(a, b) < 1e-5
+            assert U.maxerr(a, b) < 5e-5                 # dQ: fp32 reduce-add order depends on the chunking
 
 
 @pytest.mark.parametrize("shape", [(1, 2, 100, 64), (1, 2, 200, 128), (2, 1, 129, 32)], ids=lambda s: "B%d_H%d_S%d_D%d" % s)
@@ -365,10 +366,11 @@ def test_cupy_style_arrays_go_through_the_data_ptr_branch(U, monkeypatch):
         api.forward(q, k, _FakeCuPy(torch.empty(1, 2, 100, 64, device="cuda")), stream=0)
 
 
-@pytest.mark.parametrize("shape,force", [((1, 1, 1024, 64), None), ((1, 3, 1536, 128), "2"), ((2, 1, 700, 32), "2")],
-                         ids=["B1_H1_S1024_D64-auto", "B1_H3_S1536_D128-forced", "B2_H1_S700_D32-forced"])
+@pytest.mark.parametrize("shape,force", [((1, 1, 1024, 64), "2"), ((1, 3, 1536, 128), "2"), ((2, 1, 700, 32), "2")],
+                         ids=["B1_H1_S1024_D64", "B1_H3_S1536_D128", "B2_H1_S700_D32"])
 def test_host_api_sequence_split_two_gpus(U, shape, force, monkeypatch):
-    """Fewer (b,h) slabs than devices (or FA2_SEQ_SPLIT): the devices of a group split the ROWS -- forward on a range of
+    """Sequence split (chosen for very long sequences with fewer slabs than devices; forced here with FA2_SEQ_SPLIT): the
+    devices of a group split the ROWS -- forward on a range of
     query rows per device, backward on the same range of key/value rows, partial dQ summed by P2P loads over NVLink
     (the one collective of the design).  All three modes must reproduce the one-GPU results."""
     import torch

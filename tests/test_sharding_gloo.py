@@ -77,8 +77,9 @@ def _seq_worker(rank, world, port, shape, out_dir):
     BH, S, D = shape
     rng = np.random.default_rng(7)
     Q, K, V, dO = (rng.standard_normal((BH, S, D)) for _ in range(4))
+    os.environ["FA2_SEQ_SPLIT"] = str(world)                       # (a 1024-row slab is one round of work: not split by default)
     g_bh, g_s = fa2_b200.plan_split(BH, S, world)
-    assert (g_bh, g_s) == (1, world)                              # one slab, two devices -> rows are split
+    assert (g_bh, g_s) == (1, world)
     r0, r1 = fa2_b200.seq_range(S, g_s, rank)
     sc = 1.0 / np.sqrt(D)
     # forward on the own query rows
@@ -126,13 +127,21 @@ def test_two_rank_sequence_split_with_dq_reduce_matches_unsplit(tmp_path):
 
 def test_split_planner_and_row_ranges():
     import fa2_b200
+    os.environ.pop("FA2_SEQ_SPLIT", None)
     assert fa2_b200.plan_split(256, 4096, 8) == (8, 1)          # config C: plenty of slabs, plain slab split
-    assert fa2_b200.plan_split(16, 16384, 8) == (8, 1)          # config D: two slabs per device, no gain from splitting rows
-    assert fa2_b200.plan_split(4, 16384, 8) == (4, 2)           # fewer slabs than devices
-    assert fa2_b200.plan_split(1, 16384, 8) == (1, 8)
-    assert fa2_b200.plan_split(12, 8192, 8) == (4, 2)           # 12 slabs on 8 devices: 3 slabs x half the rows beat 2 / 1
+    assert fa2_b200.plan_split(16, 16384, 8) == (8, 1)          # config D: two slabs per device
+    assert fa2_b200.plan_split(12, 8192, 8) == (8, 1)           # a slab per device or more: never replicate inputs over PCIe
+    assert fa2_b200.plan_split(4, 16384, 8) == (4, 1)           # 64 forward items per slab: one round on one device anyway
+    assert fa2_b200.plan_split(1, 16384, 8) == (1, 1)
+    assert fa2_b200.plan_split(1, 131072, 8) == (1, 8)          # 512 forward / 1024 backward items: split until a share is one round
+    assert fa2_b200.plan_split(2, 65536, 8) == (2, 4)
     assert fa2_b200.plan_split(1, 300, 8) == (1, 1)             # too short to split: one device
     assert fa2_b200.plan_split(3, 4096, 1) == (1, 1)
+    os.environ["FA2_SEQ_SPLIT"] = "8"
+    assert fa2_b200.plan_split(16, 16384, 8) == (1, 8)          # forced (tools/seq_split_bench.py measures it)
+    os.environ["FA2_SEQ_SPLIT"] = "2"
+    assert fa2_b200.plan_split(16, 16384, 8) == (4, 2)
+    os.environ.pop("FA2_SEQ_SPLIT", None)
     for S, parts in ((16384, 8), (4096, 2), (1000, 2), (700, 2)):
         ranges = [fa2_b200.seq_range(S, parts, p) for p in range(parts)]
         assert ranges[0][0] == 0 and ranges[-1][1] == S
