@@ -67,9 +67,9 @@ EncodeTiledFn get_encode_fn() {
 // Descriptors are a pure function of (base, geometry, type): a small per-thread cache saves the 4 + 7 driver calls
 // per forward + backward call when the same tensors come back (training loops, the harness's timed repeats).
 struct TmapKey {
-    const void* base; int BH, S, pitch, D, kind;      // kind: 0 = fp16 copy, 1 = bf16 copy, 2 = fp32 tensor
+    const void* base; int BH, S, pitch, D, kind, box_rows;      // kind: 0 = fp16 copy, 1 = bf16 copy, 2 = fp32 tensor
     bool operator==(const TmapKey& o) const {
-        return base == o.base && BH == o.BH && S == o.S && pitch == o.pitch && D == o.D && kind == o.kind;
+        return base == o.base && BH == o.BH && S == o.S && pitch == o.pitch && D == o.D && kind == o.kind && box_rows == o.box_rows;
     }
 };
 struct TmapCache {
@@ -92,7 +92,7 @@ thread_local TmapCache g_tmaps;
 // rows are a row range of slabs that are pitch_rows apart in memory (base points at the first row of the range).
 int make_tmap_16(CUtensorMap* tm, void* base, int BH, int S, int DP, int box_rows, int bf16, int pitch_rows = 0) {
     if (pitch_rows <= 0) pitch_rows = S;
-    const TmapKey k{base, BH, S, pitch_rows, DP, bf16 ? 1 : 0};
+    const TmapKey k{base, BH, S, pitch_rows, DP, bf16 ? 1 : 0, box_rows};
     if (const CUtensorMap* hit = g_tmaps.find(k)) { *tm = *hit; return FA2_OK; }
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return fail(FA2_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
@@ -109,15 +109,15 @@ int make_tmap_16(CUtensorMap* tm, void* base, int BH, int S, int DP, int box_row
 }
 
 // fp32 [BH][S][D] tensor addressed by the dQ reduce-add: box {32 cols, 128 rows, 1 slab}, 128-byte swizzle.
-int make_tmap_f32(CUtensorMap* tm, void* base, int BH, int S, int D, int pitch_rows = 0) {
+int make_tmap_f32(CUtensorMap* tm, void* base, int BH, int S, int D, int pitch_rows = 0, int box_rows = 128) {
     if (pitch_rows <= 0) pitch_rows = S;
-    const TmapKey k{base, BH, S, pitch_rows, D, 2};
+    const TmapKey k{base, BH, S, pitch_rows, D, 2, box_rows};
     if (const CUtensorMap* hit = g_tmaps.find(k)) { *tm = *hit; return FA2_OK; }
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return fail(FA2_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
     cuuint64_t dims[3] = {static_cast<cuuint64_t>(D), static_cast<cuuint64_t>(S), static_cast<cuuint64_t>(BH)};
     cuuint64_t strides[2] = {static_cast<cuuint64_t>(D) * 4, static_cast<cuuint64_t>(pitch_rows) * D * 4};
-    cuuint32_t box[3] = {32, 128, 1};
+    cuuint32_t box[3] = {32, static_cast<cuuint32_t>(box_rows), 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -348,6 +348,11 @@ int run_bwd_main(const Prepared& pr, float* dQ, float* dK, float* dV, cudaStream
     if ((rc = make_tmap_16(&p.tm_v, pr.work + pr.wl.off_v + h0, pr.BH, Skv, pr.DP, 128, pr.bf16, pr.S))) return rc;
     if ((rc = make_tmap_16(&p.tm_do, pr.work + pr.wl.off_do, pr.BH, pr.S, pr.DP, 128, pr.bf16))) return rc;
     if ((rc = make_tmap_f32(&p.tm_dq, dQ, pr.BH, pr.S, pr.D))) return rc;
+    if (bwd_uses_pair(pr.D)) {
+        if ((rc = make_tmap_16(&p.tm_q64, pr.work + pr.wl.off_q, pr.BH, pr.S, pr.DP, 64, pr.bf16))) return rc;
+        if ((rc = make_tmap_16(&p.tm_do64, pr.work + pr.wl.off_do, pr.BH, pr.S, pr.DP, 64, pr.bf16))) return rc;
+        if ((rc = make_tmap_f32(&p.tm_dq64, dQ, pr.BH, pr.S, pr.D, 0, 64))) return rc;
+    }
     if ((rc = make_tmap_f32(&p.tm_dk, dK + e0, pr.BH, Skv, pr.D, pr.S))) return rc;
     if ((rc = make_tmap_f32(&p.tm_dv, dV + e0, pr.BH, Skv, pr.D, pr.S))) return rc;
     p.lse_log2 = lse2; p.delta = delta; p.dQ = dQ; p.dK = dK + e0; p.dV = dV + e0;

@@ -573,6 +573,7 @@ fa2_bwd_kernel(const __grid_constant__ BwdParams p) {
 }  // namespace
 
 cudaError_t launch_bwd(const BwdParams& p, cudaStream_t st) {
+    if (bwd_uses_pair(p.D)) return launch_bwd2(p, st);
     const int DP = padded_head_dim(p.D);
     const int n_tiles = (p.S_kv + BT - 1) / BT;
     // persistent: one CTA per SM (or fewer when there is less work), each walks its share of the work items
@@ -606,7 +607,8 @@ cudaError_t warm_bwd() {
     if ((e = cudaFuncGetAttributes(&a, fa2_bwd_kernel<64, false>)) != cudaSuccess) return e;
     if ((e = cudaFuncGetAttributes(&a, fa2_bwd_kernel<128, false>)) != cudaSuccess) return e;
     if ((e = cudaFuncGetAttributes(&a, fa2_bwd_kernel<64, true>)) != cudaSuccess) return e;
-    return cudaFuncGetAttributes(&a, fa2_bwd_kernel<128, true>);
+    if ((e = cudaFuncGetAttributes(&a, fa2_bwd_kernel<128, true>)) != cudaSuccess) return e;
+    return warm_bwd2();
 }
 
 }  // namespace fa2

@@ -71,6 +71,9 @@ struct BwdParams {
     CUtensorMap tm_k;
     CUtensorMap tm_v;
     CUtensorMap tm_do;
+    CUtensorMap tm_q64;  // CTA-pair kernel: Q / dO with box {64, 64, 1} (the 64 query rows one CTA feeds to S^T / dP^T)
+    CUtensorMap tm_do64;
+    CUtensorMap tm_dq64; // CTA-pair kernel: dQ with box {32, 64, 1} (each CTA reduce-adds 64 of the 128 query rows)
     CUtensorMap tm_dq;   // fp32 [BH][S][D], box {32, 128, 1}, 128B swizzle (reduce-add target)
     CUtensorMap tm_dk;   // same geometry, plain store targets
     CUtensorMap tm_dv;
@@ -144,7 +147,10 @@ cudaError_t launch_range_fix_qkv(const float* Q, const float* K, const float* V,
 cudaError_t launch_range_fix_do(const float* dO, void* dOh, size_t rows, int D, int DP, int bf16, const RangeBlock* rb,
                                 cudaStream_t st);
 cudaError_t launch_fwd(const FwdParams& p, cudaStream_t st);
-cudaError_t launch_bwd(const BwdParams& p, cudaStream_t st);
+cudaError_t launch_bwd(const BwdParams& p, cudaStream_t st);      // picks the CTA-pair kernel when bwd_uses_pair(D)
+cudaError_t launch_bwd2(const BwdParams& p, cudaStream_t st);     // fa2_bwd2_sm100.cu: cluster of two CTAs per pair of KV tiles (D = 128)
+bool bwd_uses_pair(int D);
+cudaError_t warm_bwd2();
 cudaError_t warm_fwd();
 cudaError_t warm_bwd();
 

@@ -346,6 +346,96 @@ __host__ __device__ constexpr uint32_t koff_kmajor(int k, int atom_bytes) {
 }
 __host__ __device__ constexpr uint32_t koff_mnmajor(int k) { return static_cast<uint32_t>((k * 2048) >> 4); }
 
+// ----------------------------------------------------------------------------------------
+// CTA pairs (cta_group::2): one thread of the leader CTA issues an MMA that runs on both SMs of a cluster of two; each
+// SM reads its own half of the M rows of A and its own half of the N columns of B (measured: 550 cycles per
+// 128x128x128 share against 715 SS / 594 TS for cta_group::1, tools/mma2_probe.cu; M = 128 over the pair with
+// MN-major operands and the "2x2" TMEM layout: tools/mma2b_probe.cu).  Shared-memory offsets and TMEM columns must be
+// identical in both CTAs.
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local` (a shared::cta pointer) in the CTA with the given rank of this cluster
+__device__ __forceinline__ uint32_t cluster_map(const void* local, uint32_t cta_rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(local)), "r"(cta_rank));
+    return r;
+}
+// (no .release.cluster qualifier: that form compiles to MEMBAR.ALL.GPU and costs ~2000 cycles per arrive; what the
+// pair hands over is TMEM, ordered by tcgen05.wait::st + tcgen05.fence::before_thread_sync on this side and
+// tcgen05.fence::after_thread_sync on the waiting side, or shared memory moved by the async proxy and its complete_tx)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose completion bytes are credited to a barrier given by shared::cluster address (the pair leader's)
+__device__ __forceinline__ void tma_load_3d_pair(void* smem_dst, const void* tmap, uint32_t bar_cluster_addr, int c0,
+                                                 int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+// shared memory of this CTA -> shared memory of the CTA that owns dst_cluster_addr (DSMEM, moved by the async proxy);
+// the bytes are credited to an mbarrier of the DESTINATION CTA
+__device__ __forceinline__ void dsmem_bulk_copy(uint32_t dst_cluster_addr, const void* src, uint32_t bytes,
+                                                uint32_t bar_cluster_addr) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_cluster_addr), "r"(smem_u32(src)), "r"(bytes), "r"(bar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_holder, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_holder)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// commit every prior MMA of this thread; arrives on the barrier at this smem offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3)) : "memory");
+}
+template <uint32_t A_OFF, uint32_t B_OFF>
+__device__ __forceinline__ void umma_pair_ss_off(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi,
+                                                 uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b32 al, bl;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "add.u32 al, %1, %6;\n\t"
+        "add.u32 bl, %2, %7;\n\t"
+        "mov.b64 da, {al, %3};\n\t"
+        "mov.b64 db, {bl, %3};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t"
+        "}\n"
+        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate), "n"(A_OFF), "n"(B_OFF)
+        : "memory");
+}
+template <uint32_t A_COL_OFF, uint32_t B_OFF>
+__device__ __forceinline__ void umma_pair_ts_off(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t hi,
+                                                 uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b32 at, bl;\n\t"
+        ".reg .b64 db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "add.u32 at, %1, %6;\n\t"
+        "add.u32 bl, %2, %7;\n\t"
+        "mov.b64 db, {bl, %3};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [at], db, %4, p;\n\t"
+        "}\n"
+        ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate), "n"(A_COL_OFF), "n"(B_OFF)
+        : "memory");
+}
+
 // compile-time loop: f(std::integral_constant<int, 0>{}), ..., f(integral_constant<int, N-1>{})
 template <int N, int I = 0, class F>
 __device__ __forceinline__ void static_for(F&& f) {

@@ -26,7 +26,12 @@ torch.cuda.synchronize()
 life = tl[1024:].cpu().view(n_cta, 8)
 t = tl[:1024].cpu().view(32, 32)
 names = {0: "MMA issue S", 1: "MMA ds_full(i-1) seen", 2: "MMA dq_empty(i-1) seen", 3: "MMA issue dP", 4: "MMA p_full seen/issue dV",
+         5: "MMA peer atoms landed / issue dQ(i-1) [pair kernel]", 6: "MMA dK(i-1) issued [pair kernel]",
          8: "C  s_full seen", 9: "C  p_full arrive", 10: "C  dp_full seen", 11: "C  ds_full arrive",
+         12: "C  dS math starts [pair kernel]",
+         20: "    follower C s_full seen (follower clock)", 21: "    follower C p_full arrive", 22: "    follower C dp_full seen",
+         23: "    follower C ds_full arrive", 24: "C  warpgroup 1 s_full seen", 25: "C  warpgroup 1 p_full arrive",
+         26: "    follower C warpgroup 1 s_full seen", 27: "    follower C warpgroup 1 p_full arrive",
          15: "Dr dq_full seen", 16: "Dr dq_empty arrive", 17: "Dr staging done",
          18: "Dr chunk0 issued", 19: "Dr chunk1 issued"}
 base = int(t[8, 0])
