@@ -10,10 +10,13 @@
 //     receives 64 of the 128 query rows), so each Q step reduce-adds 32 KB per SM into L2 instead of 64 KB.
 //     S^T  = K Q^T    M = 256: A = own K tile (K-major),       B = Q rows [64 r, 64 r + 64) (K-major)      -> TMEM [384,512)
 //     dP^T = V dO^T   M = 256: A = own V tile,                 B = dO rows [64 r, +64)                     -> TMEM [256,384)
-//     dV  += P^T dO   M = 256: A = P^T from TMEM,              B = dO columns [64 r, +64) (MN-major)        -> TMEM [128,256)
-//     dK  += dS^T Q   M = 256: A = dS^T from TMEM [320,384),   B = Q columns [64 r, +64) (MN-major)         -> TMEM [0,128)
+//     dV  += P^T dO   M = 256: A = P^T from TMEM [384,448),    B = dO columns [64 r, +64) (MN-major)        -> TMEM [128,256)
+//     dK  += dS^T Q   M = 256: A = dS^T from TMEM (inside dP), B = Q columns [64 r, +64) (MN-major)         -> TMEM [0,128)
 //     dQ   = dS K     M = 128: A = dS^T atoms of BOTH tiles, query columns [64 r, +64), read MN-major;
-//                              B = K columns [64 r, +64) of both tiles (MN-major)                          -> TMEM [256,320)
+//                              B = K columns [64 r, +64) of both tiles (MN-major)                          -> TMEM [448,512)
+// TMEM is full, so dQ shares columns with S^T: dQ(G-1) is issued once the compute warps have copied S^T(G) out and its
+// drain ends long before S^T(G+1) is issued -- the ~900-cycle DSMEM copy, the dQ MMA and its drain all run in the shadow
+// of the P phase instead of sitting between dS(G-1) and dP(G).
 // The dQ MMA needs, in CTA r, the dS^T atom "query half r" of the PEER's tile: the compute warpgroup that produces the
 // other half writes it to a send buffer and ships it into the peer's shared memory with one DSMEM bulk copy
 // (cp.async.bulk.shared::cluster, completion on an mbarrier of the receiver; tools/mma2b_probe.cu).  dQ lands in the
@@ -23,17 +26,17 @@
 //
 // Warp roles (16 warps): 0-3 / 4-7 compute (P^T, dS^T; warpgroup h owns query columns [64 h, +64)), 8-11 dQ drain,
 // 12 MMA issuer (leader only), 13 TMA producer (also stages LSE / D_i), 14 forwards "peer atom received" from the
-// follower to the leader, 15 register donor.  512 x 128 registers at launch; setmaxnreg: compute 160, drain 104, rest 56.
+// follower to the leader, 15 issues the DSMEM copy of the dS^T send atom.  512 x 128 registers at launch; setmaxnreg: compute 160, drain 104, rest 56.
 #include <cstdlib>
 
 #include "fa2_common.h"
 #include "ptx.cuh"
 
 #ifndef FA2_BWD_PAIR_DEFAULT
-#define FA2_BWD_PAIR_DEFAULT 0
+#define FA2_BWD_PAIR_DEFAULT 1
 #endif
 #ifndef FA2_BWD2_POLY_DEFAULT
-#define FA2_BWD2_POLY_DEFAULT 0
+#define FA2_BWD2_POLY_DEFAULT 1
 #endif
 
 namespace fa2 {
@@ -87,7 +90,7 @@ template <bool BF16, unsigned POLY>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 fa2_bwd2_kernel(const __grid_constant__ BwdParams p) {
     constexpr uint32_t TMEM_COLS = 512;
-    constexpr uint32_t COL_DK = 0, COL_DV = 128, COL_DP = 256, COL_DQ = 256, COL_DST = 320, COL_S = 384;
+    constexpr uint32_t COL_DK = 0, COL_DV = 128, COL_DP = 256, COL_S = 384, COL_DQ = 448;
     constexpr int KSTEPS_D = DP / 16, KSTEPS_T = BT / 16;
 
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -114,7 +117,7 @@ fa2_bwd2_kernel(const __grid_constant__ BwdParams p) {
     uint64_t* dq_empty = bars + 20;     // [leader] 8 drain warps
     uint64_t* dkdv_full = bars + 21;
     uint64_t* epi_issued = bars + 22;
-    uint64_t* dp_read = bars + 23;      // [leader] 16 compute warps have copied dP^T out of TMEM
+    uint64_t* s_read = bars + 23;       // [leader] 16 compute warps have copied S^T out of TMEM
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + L::OFF_TMEM_PTR);
     float* lse_s = reinterpret_cast<float*>(smem + L::OFF_LSE);
     float* delta_s = reinterpret_cast<float*>(smem + L::OFF_DELTA);
@@ -143,7 +146,7 @@ fa2_bwd2_kernel(const __grid_constant__ BwdParams p) {
             mbar_init(s_full, 2);             // tcgen05.commit (multicast) + this CTA's producer warp (LSE / D_i staged)
             mbar_init(p_full, 16);
             mbar_init(ds_full, 16);
-            mbar_init(dp_read, 16);
+            mbar_init(s_read, 16);
             mbar_init(dq_empty, 8);
             mbar_init(epi_issued, 2);
             fence_mbar_init();
@@ -250,7 +253,7 @@ fa2_bwd2_kernel(const __grid_constant__ BwdParams p) {
             const uint32_t qn_k = umma_desc_lo(smem_u32(smem + L::OFF_QN), 16), don_k = umma_desc_lo(smem_u32(smem + L::OFF_DON), 16);
             const uint32_t qd_mn = umma_desc_lo(smem_u32(smem + L::OFF_QD), ATOM), dod_mn = umma_desc_lo(smem_u32(smem + L::OFF_DOD), ATOM);
             const uint32_t dqa_mn = umma_desc_lo(smem_u32(smem + L::OFF_DQA), ATOM), kb_mn = umma_desc_lo(smem_u32(smem + L::OFF_KB), ATOM);
-            const uint32_t tS = tmem_base + COL_S, tDP = tmem_base + COL_DP, tDQ = tmem_base + COL_DQ, tDST = tmem_base + COL_DST;
+            const uint32_t tS = tmem_base + COL_S, tDP = tmem_base + COL_DP, tDQ = tmem_base + COL_DQ;
             const uint32_t tDK = tmem_base + COL_DK, tDV = tmem_base + COL_DV;
 
             auto issue_s = [&]() {
@@ -265,16 +268,16 @@ fa2_bwd2_kernel(const __grid_constant__ BwdParams p) {
                     umma_pair_ss_off<koff_kmajor(k, ATOM), koff_kmajor(k, HATOM)>(tDP, v_k, don_k, hi, id_ss, k > 0);
                 });
             };
-            auto issue_dv = [&](bool first) {       // P^T: two 32-column runs of the S region (one per compute warpgroup)
+            auto issue_dv = [&](bool first) {       // P^T: the first 64 columns of the S region
                 static_for<KSTEPS_T>([&](auto kk) {
                     constexpr int k = decltype(kk)::value;
-                    umma_pair_ts_off<(k >> 2) * 64 + (k & 3) * 8, koff_mnmajor(k)>(tDV, tS, dod_mn, hi, id_kmn, (!first || k > 0) ? 1u : 0u);
+                    umma_pair_ts_off<k * 8, koff_mnmajor(k)>(tDV, tS, dod_mn, hi, id_kmn, (!first || k > 0) ? 1u : 0u);
                 });
             };
-            auto issue_dk = [&](bool first) {       // dS^T: 64 columns behind the dQ accumulator
+            auto issue_dk = [&](bool first) {       // dS^T: two 32-column runs of the dP region (one per compute warpgroup)
                 static_for<KSTEPS_T>([&](auto kk) {
                     constexpr int k = decltype(kk)::value;
-                    umma_pair_ts_off<k * 8, koff_mnmajor(k)>(tDK, tDST, qd_mn, hi, id_kmn, (!first || k > 0) ? 1u : 0u);
+                    umma_pair_ts_off<(k >> 2) * 64 + (k & 3) * 8, koff_mnmajor(k)>(tDK, tDP, qd_mn, hi, id_kmn, (!first || k > 0) ? 1u : 0u);
                 });
             };
             auto issue_dq = [&]() {                 // contraction over the 256 KV rows of the pair: tile 0 atoms, then tile 1
@@ -284,11 +287,9 @@ fa2_bwd2_kernel(const __grid_constant__ BwdParams p) {
                     umma_pair_ss_off<off, off>(tDQ, dqa_mn, kb_mn, hi, id_dq, k > 0);
                 });
             };
-            // Issue order per step G (TMEM: dQ [256,320) and dS^T [320,384) alias dP^T [256,384)):
-            //   S(G)  |  dK(G-1)  |  dP(G)  |  dV(G)  |  dQ(G-1)
-            // dK(G-1) consumes dS^T(G-1) before dP(G) overwrites it; dQ(G-1) -- which needs the peer's dS^T atom, a
-            // ~900-cycle DSMEM copy -- goes in only after the compute warps have copied dP(G) out of TMEM (dp_read),
-            // so neither that copy nor the dQ drain sits between dS(G-1) and dP(G) (the compute warps' critical path).
+            // Issue order per step G:   S(G)  |  dK(G-1)  |  dP(G)  |  dQ(G-1)  |  dV(G)
+            // dK(G-1) consumes dS^T(G-1) before dP(G) overwrites it; dQ(G-1) lands in the upper half of the S region once
+            // the compute warps have copied S^T(G) out (s_read) and is drained before S^T(G+1) is issued.
             auto issue_tail_dk = [&](int w, int i, int Gp, bool first) {
                 (void)w; (void)i;
                 mbar_wait_spin(ds_full, Gp & 1);
@@ -329,6 +330,11 @@ fa2_bwd2_kernel(const __grid_constant__ BwdParams p) {
                 for (int i = 0; i < n_q; ++i) {
                     const int G = G0 + i;
                     mbar_wait_spin(qn_full, G & 1);
+                    if (dq_waited < dq_issued) {                // the last dQ issued has left TMEM: S^T may overwrite its columns
+                        mbar_wait_spin(dq_empty, dq_issued & 1);
+                        dq_waited = dq_issued;
+                        TL(2);
+                    }
                     tc_fence_after();
                     TL(0);
                     if (elect_one()) {
@@ -338,11 +344,6 @@ fa2_bwd2_kernel(const __grid_constant__ BwdParams p) {
                     }
                     __syncwarp();
                     if (i > 0) issue_tail_dk(w, i, G - 1, i == 1);
-                    if (dq_waited < dq_issued) {                // the last dQ issued has left TMEM: dP may overwrite its columns
-                        mbar_wait_spin(dq_empty, dq_issued & 1);
-                        dq_waited = dq_issued;
-                        TL(2);
-                    }
                     mbar_wait_spin(don_full, G & 1);
                     tc_fence_after();
                     TL(3);
@@ -352,6 +353,11 @@ fa2_bwd2_kernel(const __grid_constant__ BwdParams p) {
                         umma_commit_pair(don_empty);
                     }
                     __syncwarp();
+                    mbar_wait_spin(s_read, G & 1);              // (every step: keeps the barrier's phases in step)
+                    if (i > 0) {
+                        issue_tail_dq(w, i, G - 1, false);
+                        dq_issued = G - 1;
+                    }
                     mbar_wait_spin(p_full, G & 1);
                     mbar_wait_spin(dod_full, G & 1);
                     tc_fence_after();
@@ -361,11 +367,6 @@ fa2_bwd2_kernel(const __grid_constant__ BwdParams p) {
                         umma_commit_pair(dod_empty);
                     }
                     __syncwarp();
-                    mbar_wait_spin(dp_read, G & 1);             // (every step: keeps the barrier's phases in step)
-                    if (i > 0) {
-                        issue_tail_dq(w, i, G - 1, false);
-                        dq_issued = G - 1;
-                    }
                 }
                 issue_tail_dk(w, n_q, G0 + n_q - 1, n_q == 1);
                 issue_tail_dq(w, n_q, G0 + n_q - 1, true);
@@ -395,16 +396,14 @@ fa2_bwd2_kernel(const __grid_constant__ BwdParams p) {
         const int h = warp >> 2;                               // which 64 Q-columns of the tile
         const int n = (warp & 3) * 32 + lane;                  // kv row within the own tile == TMEM lane
         const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
-        const uint32_t tS = tmem_base + lane_addr + COL_S + h * 64;
-        const uint32_t tDP = tmem_base + lane_addr + COL_DP + h * 64;
-        const uint32_t tDST = tmem_base + lane_addr + COL_DST + h * 32;
+        const uint32_t tS = tmem_base + lane_addr + COL_S + h * 64;      // this warpgroup's S^T columns
+        const uint32_t tPT = tmem_base + lane_addr + COL_S + h * 32;     // its P^T (16 bit): [384,448) holds both warpgroups'
+        const uint32_t tDP = tmem_base + lane_addr + COL_DP + h * 64;    // its dP^T columns, then (first 32) its dS^T
         const float c2 = p.range != nullptr ? __ldg(p.range + kC2) : p.scale_log2;
         const float2 c2v = make_float2(c2, c2);
         const bool keep_local = static_cast<uint32_t>(h) == rank;            // this warpgroup's dS^T atom feeds this CTA's half of dQ
         uint8_t* ds_atom = keep_local ? smem + L::OFF_DQA + rank * ATOM : smem + L::OFF_SEND;
-        const uint32_t peer_dqa = cluster_map(smem + L::OFF_DQA + rank * ATOM, rank ^ 1);
-        const uint32_t peer_recv = cluster_map(dqa_recv, rank ^ 1);
-        const uint32_t p_full_l = cluster_map(p_full, 0), ds_full_l = cluster_map(ds_full, 0), dp_read_l = cluster_map(dp_read, 0);
+        const uint32_t p_full_l = cluster_map(p_full, 0), ds_full_l = cluster_map(ds_full, 0), s_read_l = cluster_map(s_read, 0);
         const bool issuer = ((warp & 3) == 0) && lane == 0;    // owns this warpgroup's dK / dV store groups
         const uint32_t ep_bar = 5 + 2 * h;                      // named barriers private to this warpgroup
 
@@ -438,6 +437,10 @@ fa2_bwd2_kernel(const __grid_constant__ BwdParams p) {
                 tmem_ld32(tS, sr[0]);
                 tmem_ld32(tS + 32, sr[1]);
                 tmem_wait_ld();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) { if (rank == 0) mbar_arrive(s_read); else mbar_arrive_cluster(s_read_l); }   // dQ(G-1) may take S^T's upper columns
+                named_bar_sync(9, 256);     // both warpgroups have copied S^T out: P^T of warpgroup 1 goes into warpgroup 0's columns
 #pragma unroll
                 for (int sub = 0; sub < 2; ++sub) {
 #pragma unroll
@@ -464,7 +467,7 @@ fa2_bwd2_kernel(const __grid_constant__ BwdParams p) {
 #pragma unroll
                 for (int x = 0; x < 32; ++x) pk[x] &= kv_keep;
             }
-            tmem_st32(tS, pk);                                  // over the S columns this thread already consumed
+            tmem_st32(tPT, pk);                                 // over S^T columns both warpgroups have consumed
             tmem_wait_st();
             tc_fence_before();
             __syncwarp();
@@ -480,8 +483,6 @@ fa2_bwd2_kernel(const __grid_constant__ BwdParams p) {
             tmem_ld32(tDP + 32, dr[1]);
             tmem_wait_ld();
             tc_fence_before();
-            __syncwarp();
-            if (lane == 0) { if (rank == 0) mbar_arrive(dp_read); else mbar_arrive_cluster(dp_read_l); }   // dQ(G-1) may take dP's columns
             if (warp == 0) TL(12);
             // dS^T = P^T o (dP^T - D_i): the difference in fp32, the product in packed 16-bit, kept in registers until
             // the previous step's dQ is done with the shared-memory atoms
@@ -513,28 +514,23 @@ fa2_bwd2_kernel(const __grid_constant__ BwdParams p) {
 #pragma unroll
                 for (int x = 0; x < 32; ++x) dsp[x] &= kv_keep;
             }
-            // dS^T goes into dP^T's upper 64 columns, which the OTHER warpgroup reads: for i > 0, ds_empty(G-1) below says
-            // dQ(G-1) is complete, and that was issued only after dp_read(G), i.e. after all 16 warps had copied dP^T(G)
-            // out; the first step of an item has no such chain and synchronises the two warpgroups directly.
-            if (i == 0) named_bar_sync(9, 256);
             if (G > 0) mbar_wait(ds_empty, (G - 1) & 1);        // dQ(G-1) is done with the dS^T atoms (of both CTAs)
             if (i == 0 && it > 0) {
                 // ... and so has the previous item's last dK / dV store, which was staged in this warpgroup's atom
                 if (issuer) tma_store_wait_read<0>();
                 named_bar_sync(ep_bar, 128);
             }
-            // one copy to TMEM (A of dK), one to the shared-memory atom that feeds dQ
-            tmem_st32(tDST, dsp);
+            // one copy to TMEM (A of dK; over this warpgroup's own dP^T columns), one to the shared-memory atom that feeds dQ
+            tmem_st32(tDP, dsp);
 #pragma unroll
             for (int c8 = 0; c8 < 8; ++c8)
                 *reinterpret_cast<uint4*>(ds_atom + swz128(n, c8)) = make_uint4(dsp[c8 * 4], dsp[c8 * 4 + 1], dsp[c8 * 4 + 2], dsp[c8 * 4 + 3]);
             tmem_wait_st();
             fence_proxy_async_smem();       // dS smem writes -> visible to the async proxy (tensor core / bulk copy)
             tc_fence_before();
-            if (!keep_local) {
-                named_bar_sync(10, 128);    // the whole atom is written: ship it into the peer's dQ operand buffer
-                if (issuer) dsmem_bulk_copy(peer_dqa, ds_atom, ATOM, peer_recv);
-            }
+            // the whole atom is written: warp 15 ships it into the peer's dQ operand buffer (issuing the 16 KB bulk copy
+            // blocks the issuing thread for several hundred cycles, which a compute warp cannot afford)
+            if (!keep_local) named_bar_arrive(10, 160);
             __syncwarp();
             if (lane == 0) { if (rank == 0) mbar_arrive(ds_full); else mbar_arrive_cluster(ds_full_l); }
             if (warp == 0) { TL(11); TLF(23); }
@@ -639,7 +635,17 @@ fa2_bwd2_kernel(const __grid_constant__ BwdParams p) {
         }
         if (issuer) tma_store_wait<0>();
     } else {
-        setmaxnreg_dec<56>();               // warp 15: register donor only
+        // ------------------------------------------------------------------ warp 15: ships this CTA's dS^T send atom to the peer
+        setmaxnreg_dec<56>();
+        const uint32_t peer_dqa = cluster_map(smem + L::OFF_DQA + rank * ATOM, rank ^ 1);
+        const uint32_t peer_recv = cluster_map(dqa_recv, rank ^ 1);
+        for (int w = unit; w < n_work; w += n_units) {
+            for (int i = 0; i < n_q; ++i) {
+                named_bar_sync(10, 160);    // the sending warpgroup has written (and proxy-fenced) the atom
+                if (elect_one()) dsmem_bulk_copy(peer_dqa, smem + L::OFF_SEND, ATOM, peer_recv);
+                __syncwarp();
+            }
+        }
     }
 
     tc_fence_before();
