@@ -12,14 +12,8 @@
 #include "../cuda-flash-attention_b200/csrc/ptx.cuh"
 using namespace fa2;
 
-__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync() {
     asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t cluster_map(const void* local, uint32_t rank) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(local)), "r"(rank));
-    return r;
 }
 __device__ __forceinline__ void tmem_alloc2(uint32_t* holder, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(holder)), "r"(ncols) : "memory");
@@ -35,11 +29,6 @@ __device__ __forceinline__ void umma_commit2(uint64_t* bar, uint16_t mask) {
 __device__ __forceinline__ void umma2_ss(uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
                  ::"r"(d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
-}
-// smem (this CTA) -> smem of the CTA that owns dst_cluster_addr; completion bytes go to an mbarrier of that CTA
-__device__ __forceinline__ void dsmem_bulk_copy(uint32_t dst_cluster_addr, const void* src, uint32_t bytes, uint32_t bar_cluster_addr) {
-    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst_cluster_addr), "r"(smem_u32(src)), "r"(bytes), "r"(bar_cluster_addr) : "memory");
 }
 
 // A tile [128 k rows][64 m] fp16, 128B-swizzled MN-major atom (16 KB); value A[k][m]
