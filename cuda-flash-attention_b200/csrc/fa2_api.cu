@@ -262,10 +262,9 @@ int run_cast(const Prepared& pr, const float* Q, const float* K, const float* V,
     return FA2_OK;
 }
 
-// Problems of a few MB per tensor: one cooperative launch does amax + scale decision + cast (+ dO cast and dQ
-// zero-fill when dO is given) -- the always-launched re-cast kernels would cost more than the cast itself there.
-constexpr size_t kSmallElems = size_t(2) << 20;          // 16-bit elements per tensor
-bool is_small(const Prepared& pr) { return pr.rows * pr.DP <= kSmallElems; }
+// Problems of up to ~1.2 M elements per tensor: one cooperative launch does amax + scale decision + cast (+ dO cast
+// and dQ zero-fill when dO is given) -- the always-launched re-cast kernels would cost more than the cast itself there.
+bool is_small(const Prepared& pr) { return cast_small_fits(pr.rows, pr.DP, sm_count_current()); }
 
 int run_cast_small(const Prepared& pr, const float* Q, const float* K, const float* V, const float* dO, float* dQ,
                    cudaStream_t st) {

@@ -486,9 +486,9 @@ fa2_bwd2_kernel(const __grid_constant__ BwdParams p) {
             if (warp == 0) TL(12);
             // dS^T = P^T o (dP^T - D_i): the difference in fp32, the product in packed 16-bit, kept in registers until
             // the previous step's dQ is done with the shared-memory atoms
-            uint32_t dsp[32];
-#pragma unroll
-            for (int sub = 0; sub < 2; ++sub) {
+            uint32_t dsp[2][16];
+            auto ds_math = [&](auto subc) {                     // 32 of this warpgroup's 64 query columns
+                constexpr int sub = decltype(subc)::value;
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {
                     float4 d4[4];
@@ -504,27 +504,38 @@ fa2_bwd2_kernel(const __grid_constant__ BwdParams p) {
                             const float2 t0 = __fadd2_rn(make_float2(__uint_as_float(dr[sub][c]), __uint_as_float(dr[sub][c + 1])), make_float2(-dd.x, -dd.y));
                             const float2 t1 = __fadd2_rn(make_float2(__uint_as_float(dr[sub][c + 2]), __uint_as_float(dr[sub][c + 3])), make_float2(-dd.z, -dd.w));
                             const uint32_t p0 = pk[sub * 16 + c8 * 4 + q2 * 2], p1 = pk[sub * 16 + c8 * 4 + q2 * 2 + 1];
-                            dsp[sub * 16 + c8 * 4 + q2 * 2] = BF16 ? mul_bf16x2(p0, pack_bf16x2(t0.x, t0.y)) : mul_half2(p0, pack_half2(t0.x, t0.y));
-                            dsp[sub * 16 + c8 * 4 + q2 * 2 + 1] = BF16 ? mul_bf16x2(p1, pack_bf16x2(t1.x, t1.y)) : mul_half2(p1, pack_half2(t1.x, t1.y));
+                            dsp[sub][c8 * 4 + q2 * 2] = BF16 ? mul_bf16x2(p0, pack_bf16x2(t0.x, t0.y)) : mul_half2(p0, pack_half2(t0.x, t0.y));
+                            dsp[sub][c8 * 4 + q2 * 2 + 1] = BF16 ? mul_bf16x2(p1, pack_bf16x2(t1.x, t1.y)) : mul_half2(p1, pack_half2(t1.x, t1.y));
                         }
                     }
                 }
-            }
-            if (ragged_kv) {
+                if (ragged_kv) {
 #pragma unroll
-                for (int x = 0; x < 32; ++x) dsp[x] &= kv_keep;
-            }
+                    for (int x = 0; x < 16; ++x) dsp[sub][x] &= kv_keep;
+                }
+            };
+            // one copy to TMEM (A of dK; over this warpgroup's own dP^T columns), one to the shared-memory atom that feeds dQ
+            auto ds_store = [&](auto subc) {
+                constexpr int sub = decltype(subc)::value;
+                tmem_st16(tDP + sub * 16, dsp[sub]);
+#pragma unroll
+                for (int c8 = 0; c8 < 4; ++c8)
+                    *reinterpret_cast<uint4*>(ds_atom + swz128(n, sub * 4 + c8)) =
+                        make_uint4(dsp[sub][c8 * 4], dsp[sub][c8 * 4 + 1], dsp[sub][c8 * 4 + 2], dsp[sub][c8 * 4 + 3]);
+            };
+            // The first half is stored while the second is computed: its STS / STTM drain behind the math instead of
+            // in front of the proxy fence below, which waits for every store of the thread (all 32 KB of the CTA's
+            // dS^T going out at once cost ~350 cycles per step there; backward -2.2 %, profiles/r02/experiments.md).
+            ds_math(std::integral_constant<int, 0>{});
             if (G > 0) mbar_wait(ds_empty, (G - 1) & 1);        // dQ(G-1) is done with the dS^T atoms (of both CTAs)
             if (i == 0 && it > 0) {
                 // ... and so has the previous item's last dK / dV store, which was staged in this warpgroup's atom
                 if (issuer) tma_store_wait_read<0>();
                 named_bar_sync(ep_bar, 128);
             }
-            // one copy to TMEM (A of dK; over this warpgroup's own dP^T columns), one to the shared-memory atom that feeds dQ
-            tmem_st32(tDP, dsp);
-#pragma unroll
-            for (int c8 = 0; c8 < 8; ++c8)
-                *reinterpret_cast<uint4*>(ds_atom + swz128(n, c8)) = make_uint4(dsp[c8 * 4], dsp[c8 * 4 + 1], dsp[c8 * 4 + 2], dsp[c8 * 4 + 3]);
+            ds_store(std::integral_constant<int, 0>{});
+            ds_math(std::integral_constant<int, 1>{});
+            ds_store(std::integral_constant<int, 1>{});
             tmem_wait_st();
             fence_proxy_async_smem();       // dS smem writes -> visible to the async proxy (tensor core / bulk copy)
             tc_fence_before();

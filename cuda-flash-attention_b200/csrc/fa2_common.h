@@ -136,8 +136,10 @@ cudaError_t launch_bwd_prepass(const float* O, const float* dO, const float* LSE
 // `seg_floats` floats, `pitch_floats` apart; the peer pointers are other GPUs' memory read over NVLink (P2P loads).
 cudaError_t launch_dq_peer_reduce(float* own, const float* const* peers, int n_peers, size_t seg_floats,
                                   size_t pitch_floats, int cnt, cudaStream_t st);
-// Small problems: ONE cooperative launch measures max|x| of Q, K, V (and dO), decides the scales behind a grid
-// barrier and casts with them (second read served by L2); with dO it also zero-fills dQ.  No re-cast kernels needed.
+// Small problems (cast_small_fits: at most one 8-element vector per thread and tensor on one 1024-thread block per
+// SM): ONE cooperative launch reads Q, K, V (and dO) once, measures max|x|, decides the scales behind a grid barrier
+// and casts from registers; with dO it also zero-fills dQ.  No re-cast kernels needed.
+bool cast_small_fits(size_t rows, int DP, int n_sm);
 cudaError_t launch_cast_small(const float* Q, const float* K, const float* V, const float* dO, void* Qh, void* Kh,
                               void* Vh, void* dOh, float* dQ_zero, size_t rows, int D, int DP, int bf16, RangeBlock* rb,
                               float scale, float scale_log2, int n_sm, cudaStream_t st);

@@ -104,10 +104,12 @@ range_fix_do_kernel(const float* __restrict__ dO, uint4* __restrict__ dOh, size_
     cast_tensor<true>(dO, dOh, rows, D, DP, bf16, sdo, nullptr);
 }
 
-// Small problems (a few MB per tensor): amax, scale decision and cast in ONE cooperative launch.  Phase 1: every block
-// publishes max|x| of its share of each tensor; grid barrier (arrive counter, block 0 decides and clears the maxima,
-// release generation); phase 2: cast with the decided scales (the fp32 data comes from L2 this time), and with
-// NT == 4 the dQ zero-fill.  Saves the two always-launched re-cast kernels, which cost more than the cast itself here.
+// Small problems (at most one 8-element vector per thread and tensor on a full grid): amax, scale decision and cast
+// in ONE cooperative launch that reads every input exactly once.  Each thread fetches its vector of all (3 or 4)
+// tensors up front -- one DRAM latency for everything -- and keeps the fp32 values in registers across the grid
+// barrier (arrive counter; block 0 decides the scales, clears the maxima and releases a generation); then it scales,
+// rounds and stores, and with dO given zero-fills its piece of dQ.  Saves the two always-launched re-cast kernels of
+// the large path, which would cost more than the cast itself here.
 struct SmallCastArgs {
     const float* src[4];
     uint4* dst[4];
@@ -117,30 +119,44 @@ struct SmallCastArgs {
     RangeBlock* rb;
     float scale, scale_log2;
 };
+constexpr int kSmallThreads = 1024;
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kSmallThreads, 1)
 cast_small_kernel(const SmallCastArgs a) {
+    __shared__ unsigned s_max[4][kSmallThreads / 32];
     __shared__ float s_scale[4];
     const unsigned gen0 = *reinterpret_cast<volatile unsigned*>(&a.rb->coop_release);   // read before arriving
     const int vec_per_row = a.DP >> 3;
     const size_t total = a.rows * vec_per_row;
-    const size_t tid = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x, nthr = static_cast<size_t>(gridDim.x) * blockDim.x;
-    for (int t = 0; t < a.nt; ++t) {
-        float m = 0.0f;
-        for (size_t i = tid; i < total; i += nthr) {
-            const size_t row = i / vec_per_row;
-            const int col = static_cast<int>(i % vec_per_row) * 8;
-            if (col < a.D) {
-                const float4 x = __ldcg(reinterpret_cast<const float4*>(a.src[t] + row * a.D + col));
-                const float4 y = __ldcg(reinterpret_cast<const float4*>(a.src[t] + row * a.D + col + 4));
-                m = fmaxf(m, fmaxf(fmaxf(fabsf(x.x), fabsf(x.y)), fmaxf(fabsf(x.z), fabsf(x.w))));
-                m = fmaxf(m, fmaxf(fmaxf(fabsf(y.x), fabsf(y.y)), fmaxf(fabsf(y.z), fabsf(y.w))));
-            }
+    const size_t i = blockIdx.x * static_cast<size_t>(kSmallThreads) + threadIdx.x;
+    const bool in = i < total;
+    const size_t row = in ? i / vec_per_row : 0;
+    const int col = in ? static_cast<int>(i % vec_per_row) * 8 : 0;
+    const bool real = in && col < a.D;                       // (padding columns of D = 32 are written as zeros)
+    float4 x[4][2];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        x[t][0] = x[t][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t < a.nt && real) {
+            x[t][0] = __ldg(reinterpret_cast<const float4*>(a.src[t] + row * a.D + col));
+            x[t][1] = __ldg(reinterpret_cast<const float4*>(a.src[t] + row * a.D + col + 4));
         }
-        block_amax(m, a.rb->amax[t]);
-        __syncthreads();                                         // block_amax's scratch is reused by the next tensor
     }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const float4 p = x[t][0], q = x[t][1];
+        float m = fmaxf(fmaxf(fabsf(p.x), fabsf(p.y)), fmaxf(fabsf(p.z), fabsf(p.w)));
+        m = fmaxf(m, fmaxf(fmaxf(fabsf(q.x), fabsf(q.y)), fmaxf(fabsf(q.z), fabsf(q.w))));
+        const unsigned w = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
+        if ((threadIdx.x & 31) == 0) s_max[t][threadIdx.x >> 5] = w;
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
+        for (int t = 0; t < a.nt; ++t) {
+            unsigned b = 0;
+            for (int w = 0; w < kSmallThreads / 32; ++w) b = s_max[t][w] > b ? s_max[t][w] : b;
+            if (b != 0u) atomicMax(&a.rb->amax[t][blockIdx.x % kAmaxLanes], b);
+        }
         __threadfence();
         atomicAdd(&a.rb->coop_arrive, 1u);
         if (blockIdx.x == 0) {
@@ -155,31 +171,26 @@ cast_small_kernel(const SmallCastArgs a) {
             while (*reinterpret_cast<volatile unsigned*>(&a.rb->coop_release) == gen0) { }
         }
         __threadfence();
+        for (int t = 0; t < 4; ++t) s_scale[t] = __ldcg(a.rb->sc + kSq + t);       // kSq, kSk, kSv, kSdo
     }
     __syncthreads();
-    if (threadIdx.x < 4) s_scale[threadIdx.x] = __ldcg(a.rb->sc + kSq + threadIdx.x);       // kSq, kSk, kSv, kSdo
-    __syncthreads();
-    for (int t = 0; t < a.nt; ++t) {
+    if (!in) return;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        if (t >= a.nt) break;
         const float s = s_scale[t];
-        for (size_t i = tid; i < total; i += nthr) {
-            const size_t row = i / vec_per_row;
-            const int col = static_cast<int>(i % vec_per_row) * 8;
-            uint4 out = make_uint4(0u, 0u, 0u, 0u);
-            if (col < a.D) {
-                const float4 x = __ldcg(reinterpret_cast<const float4*>(a.src[t] + row * a.D + col));
-                const float4 y = __ldcg(reinterpret_cast<const float4*>(a.src[t] + row * a.D + col + 4));
-                out.x = pack16(x.x * s, x.y * s, a.bf16);
-                out.y = pack16(x.z * s, x.w * s, a.bf16);
-                out.z = pack16(y.x * s, y.y * s, a.bf16);
-                out.w = pack16(y.z * s, y.w * s, a.bf16);
-                if (t == 3) {
-                    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-                    a.dq_zero[(row * a.D + col) >> 2] = z;
-                    a.dq_zero[((row * a.D + col) >> 2) + 1] = z;
-                }
-            }
-            a.dst[t][i] = out;
-        }
+        const float4 p = x[t][0], q = x[t][1];
+        uint4 out;                                            // (zeros stay zeros: the padding columns)
+        out.x = pack16(p.x * s, p.y * s, a.bf16);
+        out.y = pack16(p.z * s, p.w * s, a.bf16);
+        out.z = pack16(q.x * s, q.y * s, a.bf16);
+        out.w = pack16(q.z * s, q.w * s, a.bf16);
+        a.dst[t][i] = out;
+    }
+    if (a.nt == 4 && real) {
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        a.dq_zero[(row * a.D + col) >> 2] = z;
+        a.dq_zero[((row * a.D + col) >> 2) + 1] = z;
     }
 }
 
@@ -301,12 +312,17 @@ cudaError_t launch_cast_small(const float* Q, const float* K, const float* V, co
     a.dq_zero = reinterpret_cast<float4*>(dQ_zero);
     a.rows = rows; a.D = D; a.DP = DP; a.bf16 = bf16; a.nt = dO ? 4 : 3; a.rb = rb; a.scale = scale; a.scale_log2 = scale_log2;
     const size_t total = rows * (DP >> 3);
-    size_t blocks = (total + 255) / 256;
-    if (blocks > static_cast<size_t>(n_sm)) blocks = n_sm;      // one block per SM at most: co-resident for the grid barrier
+    size_t blocks = (total + kSmallThreads - 1) / kSmallThreads;   // one vector per thread and tensor
+    if (blocks > static_cast<size_t>(n_sm)) return cudaErrorInvalidValue;   // (the caller tests cast_small_fits)
     if (blocks == 0) blocks = 1;
     void* args[] = {&a};
     return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(cast_small_kernel), dim3(static_cast<unsigned>(blocks)),
-                                       dim3(256), args, 0, st);
+                                       dim3(kSmallThreads), args, 0, st);
+}
+
+// one block per SM at most (co-resident for the grid barrier), one 8-element vector per thread and tensor
+bool cast_small_fits(size_t rows, int DP, int n_sm) {
+    return rows * static_cast<size_t>(DP >> 3) <= static_cast<size_t>(n_sm) * kSmallThreads;
 }
 
 cudaError_t launch_dq_peer_reduce(float* own, const float* const* peers, int n_peers, size_t seg_floats,

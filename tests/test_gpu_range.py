@@ -71,7 +71,7 @@ def test_fp32_flag_keeps_fp32_range(U, case, shape):
 
 @pytest.mark.parametrize("case", ["dO_1e-7", "Q_1e6_K_1e-6", "V_1e6_dO_1e-3"])
 def test_fp32_range_on_the_large_problem_path(U, case):
-    """Problems above ~2M elements per tensor take the cast + last-block decision + re-cast kernels (and the fused
+    """Problems above ~1.2M elements per tensor take the cast + last-block decision + re-cast kernels (and the fused
     forward's donor warps for dO) instead of the single cooperative launch of the small path."""
     import torch
     import fa2_b200
