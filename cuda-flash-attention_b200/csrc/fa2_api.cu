@@ -427,12 +427,14 @@ struct PipeSet {
 };
 PipeSet g_pipes[kMaxDevices];
 
-// Chunk sizes (in slabs) of one device's share.  The host path is PCIe-bound (pinned Gen5 x16: ~45 GB/s each way
-// in duplex; the kernels of a chunk take a fraction of its transfer time), so the job takes (bytes of the busier
-// direction) / 45 GB/s plus whatever time only one direction is busy: the H2D of the first chunk and, at the end, the
-// kernels and the D2H of the last one.  Hence chunks as small as the fixed costs allow (~0.5 ms of transfer), grown
-// only until the persistent kernels (a chunk costs ceil(items / SMs) rounds of one work item each, however few SMs
-// its last round fills) keep up with the copies.
+// Chunk sizes (in slabs) of one device's share.  The host path is PCIe-bound (pinned Gen5 x16: ~48 GB/s each way in
+// duplex; the kernels of a chunk take a fraction of its transfer time), so the job takes (bytes of the busier
+// direction) / (duplex rate) plus whatever time only one direction is busy: the H2D of the first chunk and, at the end,
+// the kernels and the D2H of the last one.  Two opposing needs: copies of >= 32 MiB run at the full duplex rate
+// (tools/pcie_probe.py: 48 GB/s against 44 GB/s for 32 MiB pieces and ~35 GB/s for the 6 MiB pieces of a 3-slab
+// chunk at config C), while the head and the tail want small chunks.  Hence a geometric ramp: the smallest chunk the
+// fixed costs allow (~0.25 ms of transfer, grown until the persistent kernels -- a chunk costs ceil(items / SMs)
+// rounds of one work item each -- keep up with the copies), doubling up to the large size, and back down at the end.
 std::vector<int> plan_chunks(int count, int S, int D, bool fwd, bool bwd, int n_sm = 148) {
     std::vector<int> sizes;
     if (count <= 0) return sizes;
@@ -447,12 +449,27 @@ std::vector<int> plan_chunks(int count, int S, int D, bool fwd, bool bwd, int n_
         if (bwd) t += static_cast<double>((static_cast<long long>(c) * items_b + n_sm - 1) / n_sm) * n_steps * step_b;
         return t;
     };
-    int c = static_cast<int>(0.5e-3 / t_x + 0.999);
-    if (c < 1) c = 1;
-    if (c > count) c = count;
-    while (c < count && kernels(c) > 0.8 * t_x * c) ++c;
-    int left = count;
-    while (left > 0) { const int n = left < c ? left : c; sizes.push_back(n); left -= n; }
+    int cmin = static_cast<int>(0.25e-3 / t_x + 0.999);
+    if (cmin < 1) cmin = 1;
+    if (cmin > count) cmin = count;
+    while (cmin < count && kernels(cmin) > 0.8 * t_x * cmin) ++cmin;
+    // large chunks: every tensor's copy >= 32 MiB, but never more than 1/8 of the job (the pipeline needs chunks)
+    int cbig = static_cast<int>(33554432.0 / slab_bytes + 0.999);
+    if (cbig > count / 8) cbig = count / 8;
+    if (cbig < cmin) cbig = cmin;
+    std::vector<int> ramp;
+    int ramp_sum = 0;
+    for (long long c = cmin; c < cbig; c *= 2) { ramp.push_back(static_cast<int>(c)); ramp_sum += static_cast<int>(c); }
+    if (ramp.empty() || 2 * ramp_sum + cbig > count) {
+        // short job: equal chunks of the smallest size
+        int left = count;
+        while (left > 0) { const int n = left < cmin ? left : cmin; sizes.push_back(n); left -= n; }
+        return sizes;
+    }
+    const int mid = count - 2 * ramp_sum, n_mid = (mid + cbig - 1) / cbig;
+    sizes = ramp;
+    for (int i = 0; i < n_mid; ++i) sizes.push_back(mid / n_mid + (i < mid % n_mid ? 1 : 0));
+    for (size_t i = ramp.size(); i-- > 0;) sizes.push_back(ramp[i]);
     return sizes;
 }
 

@@ -120,7 +120,7 @@ def test_host_api_backward_default_dO_is_ones(U):
 
 def test_host_api_chunked_pipeline_matches_device_api(U):
     """fa2_host_* streams the slabs through three buffer sets in chunks (H2D / kernels / D2H overlapped);
-    80 slabs of S=1024 make three chunks (37 + 37 + 6, fa2_plan_chunks).  Results must equal the one-shot device path."""
+    80 slabs of S=1024 make eight chunks (7 x 11 + 3, fa2_plan_chunks).  Results must equal the one-shot device path."""
     import torch
     import fa2_b200
     Q, K, V, dO = U.randn_case((1, 80, 1024, 64), seed=17)
@@ -135,8 +135,8 @@ def test_host_api_chunked_pipeline_matches_device_api(U):
 
 
 def test_host_api_many_chunks_match_device_api(U):
-    """48 slabs of S=4096 are streamed as 9 + 9 + 9 + 9 + 9 + 3 (fa2_plan_chunks: sizes that fill the persistent
-    kernels' last round); every slab must land where the one-shot device path puts it."""
+    """48 slabs of S=4096 are streamed as 3 + 6 x 7 + 3 (fa2_plan_chunks: small first and last chunk, larger copies in
+    between); every slab must land where the one-shot device path puts it."""
     import torch
     import fa2_b200
     Q, K, V, dO = U.randn_case((1, 48, 4096, 64), seed=23)

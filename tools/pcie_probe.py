@@ -34,6 +34,6 @@ def run(h2d, d2h, reps=4, pieces=1):
 
 
 for name, h2d, d2h in (("H2D only", 1, 0), ("D2H only", 0, 1), ("both directions", 1, 1)):
-    for pieces in (1, 16):
+    for pieces in (1, 4, 8, 16, 32, 64):
         run(h2d, d2h, 1, pieces)
         print(f"{name:16s} pieces of {n // pieces >> 20:4d} MiB: {run(h2d, d2h, 4, pieces):6.1f} GB/s per direction")
