@@ -427,14 +427,16 @@ struct PipeSet {
 };
 PipeSet g_pipes[kMaxDevices];
 
-// Chunk sizes (in slabs) of one device's share.  The host path is PCIe-bound (pinned Gen5 x16: ~48 GB/s each way in
+// Chunk sizes (in slabs) of one device's share.  The host path is PCIe-bound (pinned Gen5 x16: ~47 GB/s each way in
 // duplex; the kernels of a chunk take a fraction of its transfer time), so the job takes (bytes of the busier
 // direction) / (duplex rate) plus whatever time only one direction is busy: the H2D of the first chunk and, at the end,
-// the kernels and the D2H of the last one.  Two opposing needs: copies of >= 32 MiB run at the full duplex rate
-// (tools/pcie_probe.py: 48 GB/s against 44 GB/s for 32 MiB pieces and ~35 GB/s for the 6 MiB pieces of a 3-slab
-// chunk at config C), while the head and the tail want small chunks.  Hence a geometric ramp: the smallest chunk the
-// fixed costs allow (~0.25 ms of transfer, grown until the persistent kernels -- a chunk costs ceil(items / SMs)
-// rounds of one work item each -- keep up with the copies), doubling up to the large size, and back down at the end.
+// the backlog of the D2H stream, which runs one chunk (+ its kernels) behind the H2D stream.  Small chunks shorten
+// head and tail but cost launches and synchronisation (3-slab chunks at config C: 35 GB/s per direction, 59 ms);
+// large ones leave a long tail (16 slabs: 2.2 ms of one-directional D2H).  Measured at config C (tools/e2e_trace.py
+// with FA2_CHUNK_BIG / FA2_CHUNK_MIN, profiles/r02/experiments.md): ~20 MiB per tensor copy (10 slabs) with a
+// geometric ramp from a ~0.4 ms first chunk is the best and the most repeatable (47.1-47.8 ms on a 47 GB/s box,
+// floor 45.7 ms).  Every chunk is grown until the persistent kernels -- a chunk costs ceil(items / SMs) rounds of one
+// work item each -- keep up with the copies.
 std::vector<int> plan_chunks(int count, int S, int D, bool fwd, bool bwd, int n_sm = 148) {
     std::vector<int> sizes;
     if (count <= 0) return sizes;
@@ -449,13 +451,15 @@ std::vector<int> plan_chunks(int count, int S, int D, bool fwd, bool bwd, int n_
         if (bwd) t += static_cast<double>((static_cast<long long>(c) * items_b + n_sm - 1) / n_sm) * n_steps * step_b;
         return t;
     };
-    int cmin = static_cast<int>(0.25e-3 / t_x + 0.999);
+    int cmin = static_cast<int>(0.4e-3 / t_x + 0.999);
     if (cmin < 1) cmin = 1;
     if (cmin > count) cmin = count;
     while (cmin < count && kernels(cmin) > 0.8 * t_x * cmin) ++cmin;
-    // large chunks: every tensor's copy >= 32 MiB, but never more than 1/8 of the job (the pipeline needs chunks)
-    int cbig = static_cast<int>(33554432.0 / slab_bytes + 0.999);
+    // large chunks: ~20 MiB per tensor copy, but never more than 1/8 of the job (the pipeline needs chunks)
+    int cbig = static_cast<int>(20971520.0 / slab_bytes + 0.999);
     if (cbig > count / 8) cbig = count / 8;
+    if (const char* e = getenv("FA2_CHUNK_BIG")) cbig = atoi(e);      // tuning knob (tools/e2e_trace.py)
+    if (const char* e = getenv("FA2_CHUNK_MIN")) cmin = atoi(e);
     if (cbig < cmin) cbig = cmin;
     std::vector<int> ramp;
     int ramp_sum = 0;

@@ -100,7 +100,7 @@ int fa2_partition(int BH, int n_parts, int part, int* bh0, int* count);
 /* The host pipeline's chunking of one device's share of `count` slabs (mode = FA2_MODE_*): writes up to
  * max_chunks chunk sizes (in slabs, in processing order) and returns the number of chunks (-1 on bad
  * arguments).  The path is PCIe-bound: small chunks at both ends shorten the one-directional head and tail,
- * chunks whose copies are >= 32 MiB per tensor in between run at the full duplex rate, with a geometric ramp
+ * chunks of ~20 MiB per tensor copy in between keep launches and the D2H backlog low, with a geometric ramp
  * from one to the other; every chunk is large enough for the kernels to keep up with the copies.
  * Pure arithmetic, no GPU needed. */
 int fa2_plan_chunks(int count, int S, int D, int mode, int* sizes, int max_chunks);
