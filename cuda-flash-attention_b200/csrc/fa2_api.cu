@@ -234,12 +234,14 @@ int prepare(Prepared* pr, int B, int H, int S, int D, int precision, bool backwa
 // optional per-kernel timing (fa2_profile_enable / fa2_profile_read)
 std::atomic<bool> g_profile{false};
 struct ProfSpan { int kind; cudaEvent_t a, b; };
+std::atomic<long long> g_kernel_launches{0};   // kernels launched inside profiled spans since the last read
 std::mutex g_prof_mu;                      // guards g_spans (the host entry points launch from one thread per device)
 std::vector<ProfSpan> g_spans;
 struct ProfScope {
     int kind; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr; bool on;
-    ProfScope(int k, cudaStream_t s) : kind(k), st(s), on(g_profile.load(std::memory_order_relaxed)) {
-        if (on) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, st); }
+    // n_kernels = kernels launched inside the span (the Q/K/V cast of the large path is two: cast + re-cast)
+    ProfScope(int k, cudaStream_t s, int n_kernels = 1) : kind(k), st(s), on(g_profile.load(std::memory_order_relaxed)) {
+        if (on) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, st); g_kernel_launches += n_kernels; }
     }
     ~ProfScope() {
         if (on) {
@@ -253,7 +255,7 @@ struct ProfScope {
 unsigned long long* g_timeline = nullptr;   // set by fa2_debug_set_timeline (debug builds)
 
 int run_cast(const Prepared& pr, const float* Q, const float* K, const float* V, cudaStream_t st) {
-    ProfScope prof(0, st);
+    ProfScope prof(0, st, 2);
     FA2_CUDA(launch_cast_qkv(Q, K, V, pr.work + pr.wl.off_q, pr.work + pr.wl.off_k, pr.work + pr.wl.off_v, pr.rows,
                              pr.D, pr.DP, pr.bf16, pr.range(), pr.scale, pr.scale_log2, st));
     // the cast's last block has decided the scales; re-cast only what does not fit fp16 as it is
@@ -1012,6 +1014,8 @@ int fa2_profile_read(float* ms, int* launches) {
     g_spans.clear();
     return FA2_OK;
 }
+
+long long fa2_profile_kernel_launches(void) { return g_kernel_launches.exchange(0); }
 
 int fa2_release_workspaces(void) {
     int prev = 0;

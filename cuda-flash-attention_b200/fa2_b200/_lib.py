@@ -38,6 +38,7 @@ SIGNATURES = {
     "fa2_release_workspaces": (_i, []),
     "fa2_profile_enable": (_i, [_i]),
     "fa2_profile_read": (_i, [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_i)]),
+    "fa2_profile_kernel_launches": (ctypes.c_longlong, []),
     "fa2_host_alloc": (ctypes.c_void_p, [ctypes.c_size_t]),
     "fa2_host_free": (None, [ctypes.c_void_p]),
 }

@@ -131,6 +131,9 @@ void fa2_host_free(void* p);
  * launches into launches[4], then clears the record.  Not thread-safe; off by default. */
 int fa2_profile_enable(int on);
 int fa2_profile_read(float* ms, int* launches);
+/* Number of KERNELS launched inside profiled spans since the previous call (a span can hold more than one:
+ * the Q/K/V cast of the large path is the cast plus the early-exit re-cast launch); resets the counter. */
+long long fa2_profile_kernel_launches(void);
 
 /* Release every per-device workspace the library holds. */
 int fa2_release_workspaces(void);
